@@ -1,0 +1,88 @@
+/* ligero_b200 -- C ABI of the B200-native Ligero commit-and-test back end.
+ *
+ * Drop-in boundary for the numeric body of NP-Eng/ligero's `LigeroCircuit::prove_inner`
+ * (reference: src/ligero/mod.rs:457-578).  The reference has no FFI seam of its own (pure Rust,
+ * compile-time generics only); these are the entry points a Rust `extern "C"` block in
+ * `src/ligero/mod.rs` would bind, one per private helper it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or an LG_ERR_* code; nothing unwinds across the boundary;
+ *     `lg_last_error(ctx)` gives the text of the last failure on that context;
+ *   - Fr = BN254 scalar field element = `uint64_t[4]`, little-endian limbs, MONTGOMERY form -- the
+ *     in-memory layout of `ark_bn254::Fr` (`Fp256<MontBackend<FrConfig,4>>`), so `&[Fr]` passes
+ *     zero-copy;  "Fr[n]" below means `const uint64_t*` pointing at 4*n limbs;
+ *   - input pointers may be host or device memory (detected with cudaPointerGetAttributes) unless a
+ *     parameter says otherwise; output pointers are host memory unless named `*_dev`;
+ *   - a context owns one CUDA stream; calls on one context are stream-ordered and the functions that
+ *     return host data synchronise that stream before returning.  One context per host thread;
+ *   - only the `LigeroMTTestParams` instantiation is implemented (Blake2s-256 column hash over
+ *     canonical bytes, identity leaf hash, SHA-256 two-to-one: src/ligero/types.rs:15-46).
+ */
+#ifndef LIGERO_B200_H
+#define LIGERO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_OK 0
+#define LG_ERR_INVALID 1
+#define LG_ERR_CUDA 2
+#define LG_ERR_NOMEM 3
+#define LG_ERR_UNSUPPORTED 4
+#define LG_ERR_STATE 5
+
+typedef struct lg_ctx lg_ctx;       /* per-GPU context: stream, twiddle/scale tables, scratch */
+typedef struct lg_matrix lg_matrix; /* committed matrix: U (R x n), leaf digests and Merkle nodes resident in HBM */
+
+/* ---- context ------------------------------------------------------------------------------- */
+int lg_version(void);
+int lg_ctx_create(int device, lg_ctx** out);
+int lg_ctx_destroy(lg_ctx* ctx);
+const char* lg_last_error(const lg_ctx* ctx);
+int lg_ctx_sync(lg_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's "gpu_launches") */
+uint64_t lg_ctx_launches(const lg_ctx* ctx);
+/* the two length-prefix conventions recalled from arkworks; default 1,1 */
+int lg_ctx_set_formats(lg_ctx* ctx, int col_len_prefix, int leaf_len_prefix);
+/* the stream the context launches on, as a cudaStream_t (for CUDA-event timing by the caller) */
+void* lg_ctx_stream(const lg_ctx* ctx);
+
+/* ---- encode + commit: replaces src/ligero/mod.rs:521-551 ------------------------------------ */
+/* (reed_solomon_interpolate 998-1002, reed_solomon_evaluate 1004-1008 per row; DenseMatrix::columns
+ *  src/matrices/mod.rs:163-167; H::evaluate per column 536-542; create_merkle_tree 544-549; root 551)
+ *   preenc_u : Fr[rows*k], row-major pre-encoding matrix [X;Y;Z;W] (host or device)
+ *   k        : power of two >= 2;  rho_inv : power of two >= 2 (the reference hard-codes 8, mod.rs:284)
+ *   root_out : 32 bytes (may be NULL)
+ * U, the leaves and the tree stay resident on the device behind *out until lg_matrix_free. */
+int lg_commit(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, uint8_t root_out[32],
+              lg_matrix** out);
+/* same work into an existing handle of identical shape (steady-state proving: no allocation) */
+int lg_recommit(lg_matrix* m, const uint64_t* preenc_u, uint8_t root_out[32]);
+int lg_matrix_free(lg_matrix* m);
+int lg_matrix_dims(const lg_matrix* m, size_t* rows, size_t* k, size_t* n);
+/* encode only (a2+a3), result left on the device; lg_matrix_hash then does a4-a6 on it */
+int lg_encode(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out);
+int lg_matrix_hash(lg_matrix* m, uint8_t root_out[32]);
+
+/* read-backs (parity tests, debugging): U rows in the reference's logical column order */
+int lg_matrix_read_rows(const lg_matrix* m, size_t row0, size_t nrows, uint64_t* out /* Fr[nrows*n] */);
+int lg_matrix_read_leaves(const lg_matrix* m, uint8_t* out /* n*32 */);
+int lg_matrix_read_nodes(const lg_matrix* m, uint8_t* out /* (n-1)*32, heap order, node 0 = root */);
+
+/* ---- batched inverse NTT (DensePolynomial coefficients from evaluations; small_domain.ifft) -- */
+/* in/out : Fr[rows * size], natural order, includes 1/size; host or device, may alias */
+int lg_intt(lg_ctx* ctx, const uint64_t* in, uint64_t* out, size_t rows, size_t size);
+
+/* ---- measured integer roofline ----------------------------------------------------------------- */
+/* Runs dependent-chain microbenchmarks at full occupancy for ~`ms_target` milliseconds each and
+ * reports sustained Montgomery multiplications/s and IMAD.WIDE.U32 (32x32+64) operations/s. */
+int lg_bench_int_peak(lg_ctx* ctx, double ms_target, double* fr_mul_per_s, double* imad_wide_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGERO_B200_H */

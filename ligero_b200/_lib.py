@@ -1,0 +1,72 @@
+"""ctypes binding of include/ligero_b200.h.  Loading fails loudly: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libligero_b200.so")
+
+_lib = None
+
+
+class LigeroB200Error(RuntimeError):
+    pass
+
+
+_ERR_NAMES = {1: "LG_ERR_INVALID", 2: "LG_ERR_CUDA", 3: "LG_ERR_NOMEM", 4: "LG_ERR_UNSUPPORTED", 5: "LG_ERR_STATE"}
+
+u64p = POINTER(c_uint64)
+u8p = POINTER(c_uint8)
+
+# name -> (restype, argtypes): exactly the symbols include/ligero_b200.h declares
+SIGNATURES = {
+    "lg_version": (c_int, []),
+    "lg_ctx_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "lg_ctx_destroy": (c_int, [c_void_p]),
+    "lg_last_error": (c_char_p, [c_void_p]),
+    "lg_ctx_sync": (c_int, [c_void_p]),
+    "lg_ctx_launches": (c_uint64, [c_void_p]),
+    "lg_ctx_set_formats": (c_int, [c_void_p, c_int, c_int]),
+    "lg_ctx_stream": (c_void_p, [c_void_p]),
+    "lg_commit": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, c_void_p, POINTER(c_void_p)]),
+    "lg_recommit": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lg_matrix_free": (c_int, [c_void_p]),
+    "lg_matrix_dims": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
+    "lg_encode": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p)]),
+    "lg_matrix_hash": (c_int, [c_void_p, c_void_p]),
+    "lg_matrix_read_rows": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
+    "lg_matrix_read_leaves": (c_int, [c_void_p, c_void_p]),
+    "lg_matrix_read_nodes": (c_int, [c_void_p, c_void_p]),
+    "lg_intt": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t]),
+    "lg_bench_int_peak": (c_int, [c_void_p, c_double, POINTER(c_double), POINTER(c_double)]),
+}
+
+
+def load():
+    """dlopen libligero_b200.so (building nothing: run `python -m ligero_b200.build` first)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LigeroB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m ligero_b200.build` (nvcc, sm_100a). "
+            "ligero_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, ctx=None, what: str = ""):
+    if status == 0:
+        return
+    msg = ""
+    if ctx is not None:
+        raw = load().lg_last_error(ctx)
+        msg = raw.decode() if raw else ""
+    raise LigeroB200Error(f"{what or 'ligero_b200 call'} failed: {_ERR_NAMES.get(status, status)} {msg}")

@@ -1,0 +1,168 @@
+"""Thin Python mirror of the C ABI: device context, committed matrix, Fr <-> limb conversion.
+
+Everything numeric happens in libligero_b200.so on the GPU; this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_size_t, c_void_p
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import LigeroB200Error, check
+
+BN254_R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_MONT_R = pow(2, 256, BN254_R)
+_MONT_RINV = pow(_MONT_R, -1, BN254_R)
+_MASK64 = (1 << 64) - 1
+
+
+def fr_to_limbs(values: Iterable[int]) -> np.ndarray:
+    """canonical integers -> uint64[len,4] Montgomery limbs (the layout of ark_bn254::Fr)."""
+    vals = list(values)
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        m = (v % BN254_R) * _MONT_R % BN254_R
+        out[i, 0] = m & _MASK64
+        out[i, 1] = (m >> 64) & _MASK64
+        out[i, 2] = (m >> 128) & _MASK64
+        out[i, 3] = m >> 192
+    return out
+
+
+def limbs_to_fr(arr: np.ndarray) -> List[int]:
+    """uint64[...,4] Montgomery limbs -> canonical integers."""
+    a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    out = []
+    for row in a.tolist():
+        m = row[0] | (row[1] << 64) | (row[2] << 128) | (row[3] << 192)
+        out.append(m * _MONT_RINV % BN254_R)
+    return out
+
+
+def _ptr(x) -> c_void_p:
+    """host numpy array, torch tensor (host or CUDA) or raw int address -> void*"""
+    if x is None:
+        return c_void_p(0)
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        assert x.is_contiguous()
+        return c_void_p(x.data_ptr())
+    return c_void_p(int(x))
+
+
+class Context:
+    """One per GPU / host thread (lg_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = c_void_p()
+        st = self.lib.lg_ctx_create(device, byref(h))
+        if st != 0:
+            raise LigeroB200Error(
+                f"lg_ctx_create(device={device}) failed with status {st}: a CUDA device is required "
+                "(ligero_b200 has no CPU fallback)")
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.lg_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.lg_ctx_sync(self.handle), self.handle, "lg_ctx_sync")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.lg_ctx_launches(self.handle))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.lg_ctx_stream(self.handle) or 0)
+
+    def set_formats(self, col_len_prefix: bool = True, leaf_len_prefix: bool = True):
+        check(self.lib.lg_ctx_set_formats(self.handle, int(col_len_prefix), int(leaf_len_prefix)), self.handle)
+
+    # ---- encode + commit -------------------------------------------------------------------
+    def commit(self, preenc_u, rows: int, k: int, rho_inv: int = 8) -> "CommittedMatrix":
+        """lg_commit: RS-encode the rows, hash the columns, build the Merkle tree."""
+        root = np.zeros(32, dtype=np.uint8)
+        h = c_void_p()
+        check(self.lib.lg_commit(self.handle, _ptr(preenc_u), rows, k, rho_inv, _ptr(root), byref(h)),
+              self.handle, "lg_commit")
+        return CommittedMatrix(self, h, bytes(root))
+
+    def encode(self, preenc_u, rows: int, k: int, rho_inv: int = 8) -> "CommittedMatrix":
+        h = c_void_p()
+        check(self.lib.lg_encode(self.handle, _ptr(preenc_u), rows, k, rho_inv, byref(h)), self.handle, "lg_encode")
+        return CommittedMatrix(self, h, None)
+
+    def intt(self, evals, rows: int, size: int, out=None):
+        if out is None:
+            out = np.empty((rows * size, 4), dtype=np.uint64)
+        check(self.lib.lg_intt(self.handle, _ptr(evals), _ptr(out), rows, size), self.handle, "lg_intt")
+        return out
+
+    def int_peak(self, ms_target: float = 50.0):
+        a, b = c_double(), c_double()
+        check(self.lib.lg_bench_int_peak(self.handle, ms_target, byref(a), byref(b)), self.handle, "lg_bench_int_peak")
+        return {"fr_mul_per_s": a.value, "imad_wide_per_s": b.value}
+
+
+class CommittedMatrix:
+    """lg_matrix: U, leaf digests and Merkle nodes resident in HBM."""
+
+    def __init__(self, ctx: Context, handle: c_void_p, root: Optional[bytes]):
+        self.ctx, self.handle, self.root = ctx, handle, root
+        r, k, n = c_size_t(), c_size_t(), c_size_t()
+        check(ctx.lib.lg_matrix_dims(handle, byref(r), byref(k), byref(n)), ctx.handle)
+        self.rows, self.k, self.n = r.value, k.value, n.value
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.lg_matrix_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def recommit(self, preenc_u) -> bytes:
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.ctx.lib.lg_recommit(self.handle, _ptr(preenc_u), _ptr(root)), self.ctx.handle, "lg_recommit")
+        self.root = bytes(root)
+        return self.root
+
+    def hash(self) -> bytes:
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.ctx.lib.lg_matrix_hash(self.handle, _ptr(root)), self.ctx.handle, "lg_matrix_hash")
+        self.root = bytes(root)
+        return self.root
+
+    def read_rows(self, row0: int, nrows: int) -> np.ndarray:
+        out = np.empty((nrows, self.n, 4), dtype=np.uint64)
+        check(self.ctx.lib.lg_matrix_read_rows(self.handle, row0, nrows, _ptr(out)), self.ctx.handle, "read_rows")
+        return out
+
+    def read_leaves(self) -> np.ndarray:
+        out = np.empty((self.n, 32), dtype=np.uint8)
+        check(self.ctx.lib.lg_matrix_read_leaves(self.handle, _ptr(out)), self.ctx.handle, "read_leaves")
+        return out
+
+    def read_nodes(self) -> np.ndarray:
+        out = np.empty((self.n - 1, 32), dtype=np.uint8)
+        check(self.ctx.lib.lg_matrix_read_nodes(self.handle, _ptr(out)), self.ctx.handle, "read_nodes")
+        return out

@@ -1,0 +1,418 @@
+// C ABI (include/ligero_b200.h) over the kernels: context, commit, read-backs, microbenchmarks.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/ligero_b200.h"
+#include "fr_host.h"
+#include "lg_internal.h"
+
+struct lg_ctx {
+  lg::Ctx c;
+  bool col_len_prefix = true;
+  bool leaf_len_prefix = true;
+};
+struct lg_matrix {
+  lg::Matrix m;
+  lg_ctx* owner = nullptr;
+};
+
+namespace lg {
+
+int set_error(Ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+int ctx_scratch(Ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_bytes) {
+    if (ctx->scratch) {
+      LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      LG_CUDA(ctx, cudaFree(ctx->scratch));
+      ctx->scratch = nullptr;
+      ctx->scratch_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&ctx->scratch, bytes);
+    if (e != cudaSuccess) return set_error(ctx, ERR_NOMEM, std::string("scratch cudaMalloc: ") + cudaGetErrorString(e));
+    ctx->scratch_bytes = bytes;
+  }
+  *out = ctx->scratch;
+  return OK;
+}
+
+// true if p is device (or managed) memory
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// logical row gather: out[i][rho*c + s] = plane[s][row0+i][c]
+__global__ void gather_rows_kernel(const Fr* __restrict__ u, size_t rows, int log_k, int rho, size_t row0,
+                                   size_t nrows, Fr* __restrict__ out) {
+  const size_t k = (size_t)1 << log_k, n = k * rho;
+  const size_t tot = nrows * n;
+  for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < tot; f += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = f / n, j = f % n;
+    const size_t s = j % rho, c = j / rho;
+    const uint4* src = reinterpret_cast<const uint4*>(u + s * rows * k + (row0 + i) * k + c);
+    uint4* dst = reinterpret_cast<uint4*>(out + f);
+    dst[0] = src[0];
+    dst[1] = src[1];
+  }
+}
+
+// ---- integer-peak microbenchmarks --------------------------------------------------------------
+__global__ void __launch_bounds__(256) bench_fr_mul_kernel(Fr* io, int iters) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fr a = io[t], b = io[t + (size_t)gridDim.x * blockDim.x];
+  Fr c = fr_add(a, b), d = fr_sub(a, b);
+  for (int i = 0; i < iters; i++) {  // 4 independent multiply chains per thread
+    a = fr_mul(a, b);
+    b = fr_mul(b, c);
+    c = fr_mul(c, d);
+    d = fr_mul(d, a);
+  }
+  io[t] = fr_add(fr_add(a, b), fr_add(c, d));
+}
+
+__global__ void __launch_bounds__(256) bench_imad_wide_kernel(uint64_t* io, int iters) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t a0 = io[t], a1 = a0 ^ 0x9e3779b97f4a7c15ull, a2 = a0 + 12345, a3 = ~a0;
+  uint64_t a4 = a0 * 3, a5 = a0 * 5, a6 = a0 * 7, a7 = a0 * 11;
+  const uint32_t m = (uint32_t)t | 1u;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {  // 8 independent chains x 8 = 64 mad.wide per iteration
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"((uint32_t)a0), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"((uint32_t)a1), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"((uint32_t)a2), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"((uint32_t)a3), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"((uint32_t)a4), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"((uint32_t)a5), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"((uint32_t)a6), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"((uint32_t)a7), "r"(m));
+    }
+  }
+  io[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+static int matrix_alloc(lg_ctx* ctx, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out) {
+  Ctx* c = &ctx->c;
+  if (!out) return set_error(c, ERR_INVALID, "null output handle");
+  if (rows == 0) return set_error(c, ERR_INVALID, "rows must be > 0");
+  if (k < 2 || (k & (k - 1))) return set_error(c, ERR_INVALID, "k must be a power of two >= 2");
+  if (rho_inv < 2 || (rho_inv & (rho_inv - 1))) return set_error(c, ERR_INVALID, "rho_inv must be a power of two >= 2");
+  int log_k = 0;
+  while (((size_t)1 << log_k) < k) log_k++;
+  lg_matrix* h = new (std::nothrow) lg_matrix();
+  if (!h) return set_error(c, ERR_NOMEM, "host allocation failed");
+  h->owner = ctx;
+  Matrix& m = h->m;
+  m.ctx = c;
+  m.rows = rows;
+  m.log_k = log_k;
+  m.rho_inv = (int)rho_inv;
+  m.k = k;
+  m.n = k * rho_inv;
+  cudaError_t e = cudaMalloc(&m.u, m.n * rows * sizeof(Fr));
+  if (e == cudaSuccess) e = cudaMalloc(&m.leaves, m.n * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&m.nodes, m.n * 32);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (m.u) cudaFree(m.u);
+    if (m.leaves) cudaFree(m.leaves);
+    if (m.nodes) cudaFree(m.nodes);
+    delete h;
+    return set_error(c, ERR_NOMEM, std::string("matrix cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  *out = h;
+  return OK;
+}
+
+// stage a host matrix on the device (second scratch region after the NTT temporary)
+static int stage_input(lg_ctx* ctx, const uint64_t* src, size_t elems, const Fr** dev, void** to_free) {
+  Ctx* c = &ctx->c;
+  *to_free = nullptr;
+  if (is_device_ptr(src)) {
+    *dev = reinterpret_cast<const Fr*>(src);
+    return OK;
+  }
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, elems * sizeof(Fr));
+  if (e != cudaSuccess) return set_error(c, ERR_NOMEM, std::string("input staging cudaMalloc: ") + cudaGetErrorString(e));
+  e = cudaMemcpyAsync(d, src, elems * sizeof(Fr), cudaMemcpyHostToDevice, c->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return set_error(c, ERR_CUDA, std::string("H2D copy: ") + cudaGetErrorString(e));
+  }
+  *dev = reinterpret_cast<const Fr*>(d);
+  *to_free = d;
+  return OK;
+}
+
+static int do_encode(lg_matrix* h, const uint64_t* preenc_u) {
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  if (!preenc_u) return set_error(c, ERR_INVALID, "null input matrix");
+  const Fr* dev;
+  void* to_free;
+  LG_TRY(stage_input(h->owner, preenc_u, m.rows * m.k, &dev, &to_free));
+  int s = encode_rows(c, dev, m.rows, m.log_k, m.rho_inv, m.u);
+  if (to_free) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(to_free);
+  }
+  return s;
+}
+
+static int do_hash(lg_matrix* h, uint8_t root_out[32]) {
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  LG_TRY(hash_columns(c, m.u, m.rows, m.log_k, m.rho_inv, m.leaves, h->owner->col_len_prefix));
+  LG_TRY(merkle_build(c, m.leaves, m.n, m.nodes, h->owner->leaf_len_prefix));
+  if (root_out) {
+    LG_CUDA(c, cudaMemcpyAsync(root_out, m.nodes, 32, cudaMemcpyDeviceToHost, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return OK;
+}
+
+}  // namespace lg
+
+using namespace lg;
+
+extern "C" {
+
+int lg_version(void) { return 1; }
+
+int lg_ctx_create(int device, lg_ctx** out) {
+  if (!out) return ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+    cudaGetLastError();
+    return ERR_CUDA;  // no usable GPU: the product has no CPU fallback
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return ERR_CUDA;
+  lg_ctx* ctx = new (std::nothrow) lg_ctx();
+  if (!ctx) return ERR_NOMEM;
+  ctx->c.device = device;
+  if (cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  *out = ctx;
+  return OK;
+}
+
+int lg_ctx_destroy(lg_ctx* ctx) {
+  if (!ctx) return OK;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  for (auto& kv : ctx->c.tables) {
+    cudaFree(kv.second.w_fwd);
+    cudaFree(kv.second.w_inv);
+    cudaFree(kv.second.scale);
+  }
+  if (ctx->c.scratch) cudaFree(ctx->c.scratch);
+  cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+  return OK;
+}
+
+const char* lg_last_error(const lg_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }
+
+int lg_ctx_sync(lg_ctx* ctx) {
+  if (!ctx) return ERR_INVALID;
+  LG_CUDA(&ctx->c, cudaStreamSynchronize(ctx->c.stream));
+  return OK;
+}
+
+uint64_t lg_ctx_launches(const lg_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int lg_ctx_set_formats(lg_ctx* ctx, int col_len_prefix, int leaf_len_prefix) {
+  if (!ctx) return ERR_INVALID;
+  ctx->col_len_prefix = col_len_prefix != 0;
+  ctx->leaf_len_prefix = leaf_len_prefix != 0;
+  return OK;
+}
+
+void* lg_ctx_stream(const lg_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+
+int lg_encode(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out) {
+  if (!ctx) return ERR_INVALID;
+  cudaSetDevice(ctx->c.device);
+  lg_matrix* h = nullptr;
+  LG_TRY(matrix_alloc(ctx, rows, k, rho_inv, &h));
+  int s = do_encode(h, preenc_u);
+  if (s != OK) {
+    lg_matrix_free(h);
+    return s;
+  }
+  *out = h;
+  return OK;
+}
+
+int lg_matrix_hash(lg_matrix* m, uint8_t root_out[32]) {
+  if (!m) return ERR_INVALID;
+  cudaSetDevice(m->m.ctx->device);
+  return do_hash(m, root_out);
+}
+
+int lg_commit(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, uint8_t root_out[32],
+              lg_matrix** out) {
+  if (!ctx) return ERR_INVALID;
+  lg_matrix* h = nullptr;
+  LG_TRY(lg_encode(ctx, preenc_u, rows, k, rho_inv, &h));
+  int s = do_hash(h, root_out);
+  if (s != OK) {
+    lg_matrix_free(h);
+    return s;
+  }
+  *out = h;
+  return OK;
+}
+
+int lg_recommit(lg_matrix* m, const uint64_t* preenc_u, uint8_t root_out[32]) {
+  if (!m) return ERR_INVALID;
+  cudaSetDevice(m->m.ctx->device);
+  LG_TRY(do_encode(m, preenc_u));
+  return do_hash(m, root_out);
+}
+
+int lg_matrix_free(lg_matrix* m) {
+  if (!m) return OK;
+  cudaSetDevice(m->m.ctx->device);
+  cudaStreamSynchronize(m->m.ctx->stream);
+  if (m->m.owns_u && m->m.u) cudaFree(m->m.u);
+  if (m->m.leaves) cudaFree(m->m.leaves);
+  if (m->m.nodes) cudaFree(m->m.nodes);
+  delete m;
+  return OK;
+}
+
+int lg_matrix_dims(const lg_matrix* m, size_t* rows, size_t* k, size_t* n) {
+  if (!m) return ERR_INVALID;
+  if (rows) *rows = m->m.rows;
+  if (k) *k = m->m.k;
+  if (n) *n = m->m.n;
+  return OK;
+}
+
+int lg_matrix_read_rows(const lg_matrix* h, size_t row0, size_t nrows, uint64_t* out) {
+  if (!h || !out) return ERR_INVALID;
+  const Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  if (row0 + nrows > m.rows) return set_error(c, ERR_INVALID, "row range out of bounds");
+  if (nrows == 0) return OK;
+  cudaSetDevice(c->device);
+  Fr* tmp;
+  LG_CUDA(c, cudaMalloc(&tmp, nrows * m.n * sizeof(Fr)));
+  gather_rows_kernel<<<1024, 256, 0, c->stream>>>(m.u, m.rows, m.log_k, m.rho_inv, row0, nrows, tmp);
+  c->launches++;
+  cudaError_t e = cudaMemcpyAsync(out, tmp, nrows * m.n * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) return set_error(c, ERR_CUDA, cudaGetErrorString(e));
+  return OK;
+}
+
+int lg_matrix_read_leaves(const lg_matrix* h, uint8_t* out) {
+  if (!h || !out) return ERR_INVALID;
+  Ctx* c = h->m.ctx;
+  cudaSetDevice(c->device);
+  LG_CUDA(c, cudaMemcpyAsync(out, h->m.leaves, h->m.n * 32, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OK;
+}
+
+int lg_matrix_read_nodes(const lg_matrix* h, uint8_t* out) {
+  if (!h || !out) return ERR_INVALID;
+  Ctx* c = h->m.ctx;
+  cudaSetDevice(c->device);
+  LG_CUDA(c, cudaMemcpyAsync(out, h->m.nodes, (h->m.n - 1) * 32, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OK;
+}
+
+int lg_intt(lg_ctx* ctx, const uint64_t* in, uint64_t* out, size_t rows, size_t size) {
+  if (!ctx || !in || !out) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  if (size < 2 || (size & (size - 1))) return set_error(c, ERR_INVALID, "size must be a power of two >= 2");
+  cudaSetDevice(c->device);
+  int log_k = 0;
+  while (((size_t)1 << log_k) < size) log_k++;
+  const size_t elems = rows * size;
+  const bool in_dev = is_device_ptr(in), out_dev = is_device_ptr(out);
+  Fr *din = (Fr*)in, *dout = (Fr*)out;
+  Fr* stage = nullptr;
+  if (!in_dev || !out_dev) {
+    LG_CUDA(c, cudaMalloc(&stage, elems * sizeof(Fr)));
+    if (!in_dev) {
+      LG_CUDA(c, cudaMemcpyAsync(stage, in, elems * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+      din = stage;
+    }
+    if (!out_dev) dout = stage;
+  }
+  int s = intt_rows(c, din, dout, rows, log_k);
+  if (s == OK && !out_dev) {
+    cudaError_t e = cudaMemcpyAsync(out, dout, elems * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream);
+    if (e != cudaSuccess) s = set_error(c, ERR_CUDA, cudaGetErrorString(e));
+  }
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  if (s == OK && e2 != cudaSuccess) s = set_error(c, ERR_CUDA, cudaGetErrorString(e2));
+  if (stage) cudaFree(stage);
+  return s;
+}
+
+int lg_bench_int_peak(lg_ctx* ctx, double ms_target, double* fr_mul_per_s, double* imad_wide_per_s) {
+  if (!ctx) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  const int blocks = c->sm_count * 8, threads = 256;  // 2048 threads / SM
+  const size_t nthreads = (size_t)blocks * threads;
+  Fr* buf;
+  LG_CUDA(c, cudaMalloc(&buf, 2 * nthreads * sizeof(Fr)));
+  LG_CUDA(c, cudaMemsetAsync(buf, 0x17, 2 * nthreads * sizeof(Fr), c->stream));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float ms = 0;
+  // Fr multiplications
+  int iters = 64;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, c->stream);
+    bench_fr_mul_kernel<<<blocks, threads, 0, c->stream>>>(buf, iters);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->launches++;
+    if (rep == 0 && ms > 0) iters = (int)(iters * ms_target / ms) + 1;
+  }
+  if (fr_mul_per_s) *fr_mul_per_s = 4.0 * iters * (double)nthreads / (ms * 1e-3);
+  // raw IMAD.WIDE.U32
+  iters = 64;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0, c->stream);
+    bench_imad_wide_kernel<<<blocks, threads, 0, c->stream>>>((uint64_t*)buf, iters);
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->launches++;
+    if (rep == 0 && ms > 0) iters = (int)(iters * ms_target / ms) + 1;
+  }
+  if (imad_wide_per_s) *imad_wide_per_s = 64.0 * iters * (double)nthreads / (ms * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(buf);
+  if (e != cudaSuccess) return set_error(c, ERR_CUDA, cudaGetErrorString(e));
+  return OK;
+}
+
+}  // extern "C"

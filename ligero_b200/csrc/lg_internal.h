@@ -1,0 +1,91 @@
+// Internal declarations shared by the kernels and the C ABI (not installed; see include/ligero_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fr.cuh"
+
+namespace lg {
+
+// ---- error plumbing: the C ABI never unwinds; every internal call returns a status ---------------
+enum Status : int {
+  OK = 0,
+  ERR_INVALID = 1,      // bad argument (shape, null pointer, unsupported size)
+  ERR_CUDA = 2,         // CUDA runtime error (see lg_last_error)
+  ERR_NOMEM = 3,
+  ERR_UNSUPPORTED = 4,
+  ERR_STATE = 5,
+};
+
+struct Ctx;
+int set_error(Ctx* ctx, int code, const std::string& msg);
+#define LG_CUDA(ctx, expr)                                                                         \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return lg::set_error((ctx), lg::ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+#define LG_TRY(expr)            \
+  do {                          \
+    int _s = (expr);            \
+    if (_s != lg::OK) return _s; \
+  } while (0)
+
+// ---- NTT tables for one (log_k, rho_inv) ------------------------------------------------------------
+struct NttTables {
+  int log_k = 0;
+  int rho_inv = 0;
+  Fr* w_fwd = nullptr;   // omega_k^i,  i < max(1, k/2)
+  Fr* w_inv = nullptr;   // omega_k^-i
+  Fr* scale = nullptr;   // (rho_inv-1) tables of k: scale[(s-1)*k + pos] = g^(s*bitrev(pos)) / k,  g = omega_{rho_inv*k}
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string last_error;
+  std::map<std::pair<int, int>, NttTables> tables;  // (log_k, rho_inv)
+  // kernel launch counter (bench.py's "gpu_launches")
+  uint64_t launches = 0;
+  // scratch reused across calls
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+int ctx_scratch(Ctx* ctx, size_t bytes, void** out);
+int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out);
+
+// ---- committed matrix ------------------------------------------------------------------------------
+// Physical layout of U (R x n, n = rho_inv*k) in HBM: rho_inv "coset planes", each R x k row-major:
+//     plane[s][i][c] = U[i][rho_inv*c + s] = p_i(g^s * omega_k^c)
+// plane 0 is the message itself (systematic positions, src/ligero/mod.rs:89).
+struct Matrix {
+  Ctx* ctx = nullptr;
+  size_t rows = 0;      // R
+  int log_k = 0;
+  int rho_inv = 0;
+  size_t k = 0, n = 0;
+  Fr* u = nullptr;          // rho_inv * R * k
+  uint8_t* leaves = nullptr;  // n * 32, logical column order
+  uint8_t* nodes = nullptr;   // (n-1) * 32, heap order, node 0 = root
+  bool owns_u = true;
+};
+
+// ---- kernel launchers (all stream-ordered on ctx->stream) -------------------------------------------
+// Reed-Solomon row encoding: msg (R x k, Montgomery, row-major, device) -> planes (a2+a3)
+int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* u_planes);
+// batched inverse NTT of `rows` rows of length 2^log_k, natural order in and out, includes 1/k
+int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k);
+// column hashing (a4+a5): leaves[j] = BLAKE2s(u64le(R) || canonical LE bytes of column j)
+int hash_columns(Ctx* ctx, const Fr* u_planes, size_t rows, int log_k, int rho_inv, uint8_t* leaves,
+                 bool len_prefix);
+// Merkle tree (a6)
+int merkle_build(Ctx* ctx, const uint8_t* leaves, size_t n, uint8_t* nodes, bool leaf_len_prefix);
+
+}  // namespace lg

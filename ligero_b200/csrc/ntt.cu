@@ -1,0 +1,420 @@
+// Reed-Solomon row encoding over BN254 Fr for sm_100a  (replaces src/ligero/mod.rs:521-533, 998-1008).
+//
+// Reference schedule: per row iFFT_k, then zero-pad to n = rho_inv*k and FFT_n.  Here (exactly the same
+// values): U[i][rho_inv*c + s] = p_i(g^s w_k^c) is the size-k NTT of the coefficients
+// scaled by g^(s*idx), g = w_n; coset 0 is the message itself.  Per row:
+//     DIF inverse NTT (natural in -> bit-reversed coefficients, no reordering pass)
+//     x (rho_inv-1):  scale by table[s][pos] = g^(s*bitrev(pos))/k   then DIT NTT (bit-reversed in -> natural)
+// A CTA keeps 2^LOG_E elements in shared memory (two 16-byte half planes, XOR-swizzled so every access
+// pattern of the radix-8 passes is bank-conflict free); each thread holds 8 elements in registers and
+// does three butterfly stages per shared-memory round trip.  Rows longer than 2^LOG_E get their top
+// stages from register-only radix-2/4/8 passes over global memory (fully coalesced: consecutive threads
+// touch consecutive 32-byte elements).  All-zero rows (about half of the witness matrix) are
+// detected at load time and short-circuited to zero stores.
+#include "fr_host.h"
+#include "lg_internal.h"
+
+namespace lg {
+
+// ------------------------------------------------------------------------------------------------
+// element load/store helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fr fr_pack(const uint4& a, const uint4& b) {
+  Fr r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {  // read-only path (tables)
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  return fr_pack(__ldg(q), __ldg(q + 1));
+}
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  return fr_pack(q[0], q[1]);
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& x) {
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  q[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ uint32_t fr_or(const Fr& x) {
+  return x.v[0] | x.v[1] | x.v[2] | x.v[3] | x.v[4] | x.v[5] | x.v[6] | x.v[7];
+}
+
+// shared memory: element i lives at 16-byte slot swz(i) of the lo plane and of the hi plane
+__device__ __forceinline__ uint32_t swz(uint32_t i) { return i ^ ((i >> 3) & 7u); }
+__device__ __forceinline__ Fr lds_fr(const uint4* lo, const uint4* hi, uint32_t i) {
+  const uint32_t p = swz(i);
+  return fr_pack(lo[p], hi[p]);
+}
+__device__ __forceinline__ void sts_fr(uint4* lo, uint4* hi, uint32_t i, const Fr& x) {
+  const uint32_t p = swz(i);
+  lo[p] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  hi[p] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// radix-2^R butterfly network on the R stages s .. s+R-1 of a size-2^q transform.
+// x[e] is the element whose index has bits (s..s+R-1) = e and low s bits = t_lo.
+//   DIT (forward): v = x1 * w^j ; (x0, x1) = (x0 + v, x0 - v)          stages ascending
+//   DIF (inverse): (x0, x1) = (x0 + x1, (x0 - x1) * w^-j)              stages descending
+// with j = index mod 2^stage and twiddle W[j << (q - stage - 1)], W the order-2^q table.
+// ------------------------------------------------------------------------------------------------
+template <int R, bool DIF>
+__device__ __forceinline__ void butterflies(Fr (&x)[1 << R], uint32_t t_lo, int s, int q,
+                                            const Fr* __restrict__ W) {
+#pragma unroll
+  for (int bb = 0; bb < R; bb++) {
+    const int b = DIF ? (R - 1 - bb) : bb;
+    const int shift = q - (s + b) - 1;
+#pragma unroll
+    for (int el = 0; el < (1 << b); el++) {
+      const uint32_t j = t_lo | ((uint32_t)el << s);
+      if (j == 0) {  // twiddle 1: no multiplication (all of stage 0, half of stage 1, ...)
+#pragma unroll
+        for (int eh = 0; eh < (1 << (R - 1 - b)); eh++) {
+          const int e0 = el | (eh << (b + 1)), e1 = e0 | (1 << b);
+          const Fr u = x[e0], v = x[e1];
+          x[e0] = fr_add(u, v);
+          x[e1] = fr_sub(u, v);
+        }
+      } else {
+        const Fr w = ldg_fr(W + ((size_t)j << shift));
+#pragma unroll
+        for (int eh = 0; eh < (1 << (R - 1 - b)); eh++) {
+          const int e0 = el | (eh << (b + 1)), e1 = e0 | (1 << b);
+          if (!DIF) {
+            const Fr u = x[e0];
+            const Fr v = fr_mul(x[e1], w);
+            x[e0] = fr_add(u, v);
+            x[e1] = fr_sub(u, v);
+          } else {
+            const Fr u = x[e0], v = x[e1];
+            x[e0] = fr_add(u, v);
+            x[e1] = fr_mul(fr_sub(u, v), w);
+          }
+        }
+      }
+    }
+  }
+}
+
+// one radix-2^R pass over E elements held in shared memory (src planes -> dst planes; may alias)
+template <int R, bool DIF, bool SCALE>
+__device__ __forceinline__ void smem_pass(const uint4* slo, const uint4* shi, uint4* dlo, uint4* dhi, int s, int q,
+                                          const Fr* __restrict__ W, const Fr* __restrict__ scale, uint32_t col_base,
+                                          uint32_t col_mask, int E, int NT) {
+  for (int g = threadIdx.x; g < (E >> R); g += NT) {
+    const uint32_t t_lo = g & ((1u << s) - 1u), t_hi = (uint32_t)g >> s;
+    const uint32_t base = (t_hi << (s + R)) | t_lo;
+    Fr x[1 << R];
+#pragma unroll
+    for (int e = 0; e < (1 << R); e++) {
+      const uint32_t idx = base | ((uint32_t)e << s);
+      x[e] = lds_fr(slo, shi, idx);
+      if (SCALE) x[e] = fr_mul(x[e], ldg_fr(scale + ((col_base + idx) & col_mask)));
+    }
+    butterflies<R, DIF>(x, t_lo, s, q, W);
+#pragma unroll
+    for (int e = 0; e < (1 << R); e++) sts_fr(dlo, dhi, base | ((uint32_t)e << s), x[e]);
+  }
+}
+
+template <bool DIF, bool SCALE>
+__device__ __forceinline__ void smem_pass_r(int r, const uint4* slo, const uint4* shi, uint4* dlo, uint4* dhi, int s,
+                                            int q, const Fr* W, const Fr* scale, uint32_t col_base, uint32_t col_mask,
+                                            int E, int NT) {
+  if (r == 3) smem_pass<3, DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
+  else if (r == 2) smem_pass<2, DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
+  else smem_pass<1, DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
+}
+
+// stage grouping: radix 8 wherever possible, never a lone radix-2 after radix-8 when 4 stages remain
+__host__ __device__ __forceinline__ int pass_radix(int remaining) { return remaining == 4 ? 2 : (remaining < 3 ? remaining : 3); }
+
+struct LocalArgs {
+  const Fr* in;         // rows*k elements (message, or output of the strided DIF passes)
+  Fr* out;              // MODE 0: U planes base;  MODE 1: coefficient output (natural order)
+  unsigned long long total;         // rows * k
+  unsigned long long plane_stride;  // rows * k
+  int q;                // log2 k
+  int l;                // local stages = min(q, LOG_E)
+  int rho;              // cosets (MODE 0)
+  int copy_plane0;      // MODE 0: also store the input to plane 0 (only when `in` is the message)
+  const Fr* w_fwd;
+  const Fr* w_inv;
+  const Fr* scale;
+  Fr kinv;              // MODE 1: 1/k
+};
+
+// MODE 0: encode (iNTT tail + all cosets).  MODE 1: iNTT tail only, scaled, natural-order output.
+template <int LOG_E, int MODE>
+__global__ void __launch_bounds__(1 << (LOG_E - 3)) ntt_local_kernel(const LocalArgs a) {
+  constexpr int E = 1 << LOG_E, NT = E / 8;
+  extern __shared__ uint4 smem[];
+  uint4 *Alo = smem, *Ahi = smem + E, *Blo = smem + 2 * E, *Bhi = smem + 3 * E;
+  const unsigned long long f0 = (unsigned long long)blockIdx.x * E;
+  const uint32_t col_mask = (1u << a.q) - 1u;
+  const uint32_t col_base = (uint32_t)(f0 & col_mask);
+
+  uint32_t nz = 0;
+  for (int i = threadIdx.x; i < E; i += NT) {
+    const unsigned long long f = f0 + i;
+    Fr x = fr_zero();
+    if (f < a.total) x = ld_fr(a.in + f);
+    nz |= fr_or(x);
+    sts_fr(Alo, Ahi, i, x);
+    if (MODE == 0 && a.copy_plane0 && f < a.total) st_fr(a.out + f, x);
+  }
+  const int any = __syncthreads_or(nz != 0);
+  if (!any) {  // all-zero rows: codeword / coefficients are zero
+    const Fr z = fr_zero();
+    if (MODE == 0) {
+      for (int s = 1; s < a.rho; s++)
+        for (int i = threadIdx.x; i < E; i += NT)
+          if (f0 + i < a.total) st_fr(a.out + s * a.plane_stride + f0 + i, z);
+    } else {
+      for (int i = threadIdx.x; i < E; i += NT)
+        if (f0 + i < a.total) st_fr(a.out + f0 + i, z);
+    }
+    return;
+  }
+
+  // inverse transform tail: DIF stages l-1 .. 0 in place in A
+  for (int top = a.l; top > 0;) {
+    const int r = pass_radix(top), s = top - r;
+    smem_pass_r<true, false>(r, Alo, Ahi, Alo, Ahi, s, a.q, a.w_inv, nullptr, 0, 0, E, NT);
+    __syncthreads();
+    top = s;
+  }
+
+  if (MODE == 1) {
+    for (int i = threadIdx.x; i < E; i += NT) {
+      const unsigned long long f = f0 + i;
+      if (f < a.total) {
+        const uint32_t col = (uint32_t)(f & col_mask);
+        const uint32_t nat = __brev(col) >> (32 - a.q);
+        st_fr(a.out + (f - col) + nat, fr_mul(lds_fr(Alo, Ahi, i), a.kinv));
+      }
+    }
+    return;
+  }
+
+  // cosets 1 .. rho-1: scale (first pass, A -> B) then DIT stages 0 .. l-1 in B
+  for (int cs = 1; cs < a.rho; cs++) {
+    const Fr* sc = a.scale + (size_t)(cs - 1) * ((size_t)1 << a.q);
+    for (int s = 0; s < a.l;) {
+      const int r = pass_radix(a.l - s);
+      if (s == 0) smem_pass_r<false, true>(r, Alo, Ahi, Blo, Bhi, 0, a.q, a.w_fwd, sc, col_base, col_mask, E, NT);
+      else smem_pass_r<false, false>(r, Blo, Bhi, Blo, Bhi, s, a.q, a.w_fwd, nullptr, 0, 0, E, NT);
+      __syncthreads();
+      s += r;
+    }
+    Fr* dst = a.out + cs * a.plane_stride + f0;
+    for (int i = threadIdx.x; i < E; i += NT)
+      if (f0 + i < a.total) st_fr(dst + i, lds_fr(Blo, Bhi, i));
+    __syncthreads();
+  }
+}
+
+// register-only radix-2^R pass over global memory for the stages s..s+R-1 (s >= local size) of every row
+template <int R, bool DIF>
+__global__ void __launch_bounds__(256) ntt_global_pass_kernel(const Fr* in, Fr* out, Fr* copy_out, int q, int s,
+                                                              const Fr* __restrict__ W) {
+  const uint32_t g = blockIdx.y * blockDim.x + threadIdx.x;
+  if (g >= (1u << (q - R))) return;
+  const size_t off = (size_t)blockIdx.x << q;
+  const uint32_t t_lo = g & ((1u << s) - 1u), t_hi = g >> s;
+  const uint32_t base = (t_hi << (s + R)) | t_lo;
+  Fr x[1 << R];
+  uint32_t nz = 0;
+#pragma unroll
+  for (int e = 0; e < (1 << R); e++) {
+    x[e] = ld_fr(in + off + (base | ((uint32_t)e << s)));
+    nz |= fr_or(x[e]);
+  }
+  if (copy_out) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); e++) st_fr(copy_out + off + (base | ((uint32_t)e << s)), x[e]);
+  }
+  if (nz == 0 && in == out) return;  // zeros stay zeros
+  if (nz != 0) butterflies<R, DIF>(x, t_lo, s, q, W);
+#pragma unroll
+  for (int e = 0; e < (1 << R); e++) st_fr(out + off + (base | ((uint32_t)e << s)), x[e]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tables and launchers
+// ------------------------------------------------------------------------------------------------
+static uint32_t bitrev_host(uint32_t x, int bits) {
+  uint32_t r = 0;
+  for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+  return r;
+}
+
+int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out) {
+  auto key = std::make_pair(log_k, rho_inv);
+  auto it = ctx->tables.find(key);
+  if (it != ctx->tables.end()) {
+    *out = &it->second;
+    return OK;
+  }
+  if (log_k < 1 || log_k > 26) return set_error(ctx, ERR_INVALID, "log_k out of range");
+  int log_rho = 0;
+  while ((1 << log_rho) < rho_inv) log_rho++;
+  if ((1 << log_rho) != rho_inv || rho_inv < 1 || log_k + log_rho > 28)
+    return set_error(ctx, ERR_INVALID, "rho_inv must be a power of two with n <= 2^28");
+  const size_t k = (size_t)1 << log_k, half = k / 2 ? k / 2 : 1;
+  std::vector<Fr> wf(half), wi(half), sc((size_t)(rho_inv - 1) * k);
+  const Fr w = fr_root_of_unity(log_k), winv = fr_inv(w);
+  wf[0] = wi[0] = fr_one();
+  for (size_t i = 1; i < half; i++) {
+    wf[i] = fr_mul(wf[i - 1], w);
+    wi[i] = fr_mul(wi[i - 1], winv);
+  }
+  const Fr g = fr_root_of_unity(log_k + log_rho);
+  const Fr kinv = fr_inv(fr_from_u64(k));
+  std::vector<Fr> pw(k);
+  Fr gs = fr_one();
+  for (int s = 1; s < rho_inv; s++) {
+    gs = fr_mul(gs, g);  // g^s
+    pw[0] = kinv;
+    for (size_t i = 1; i < k; i++) pw[i] = fr_mul(pw[i - 1], gs);
+    for (size_t pos = 0; pos < k; pos++) sc[(size_t)(s - 1) * k + pos] = pw[bitrev_host((uint32_t)pos, log_k)];
+  }
+  NttTables t;
+  t.log_k = log_k;
+  t.rho_inv = rho_inv;
+  LG_CUDA(ctx, cudaMalloc(&t.w_fwd, half * sizeof(Fr)));
+  LG_CUDA(ctx, cudaMalloc(&t.w_inv, half * sizeof(Fr)));
+  LG_CUDA(ctx, cudaMalloc(&t.scale, (sc.size() ? sc.size() : 1) * sizeof(Fr)));
+  LG_CUDA(ctx, cudaMemcpyAsync(t.w_fwd, wf.data(), half * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  LG_CUDA(ctx, cudaMemcpyAsync(t.w_inv, wi.data(), half * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  if (!sc.empty())
+    LG_CUDA(ctx, cudaMemcpyAsync(t.scale, sc.data(), sc.size() * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die at scope exit
+  auto ins = ctx->tables.emplace(key, t);
+  *out = &ins.first->second;
+  return OK;
+}
+
+constexpr int kLogE = 10;  // 1024 elements / CTA: 64 KiB of shared memory, 128 threads, 3 CTAs per SM
+
+template <int R, bool DIF>
+static int launch_global_pass(Ctx* ctx, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s, const Fr* W) {
+  const uint32_t groups = 1u << (q - R);
+  const uint32_t bs = groups < 256 ? groups : 256;
+  dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
+  ntt_global_pass_kernel<R, DIF><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W);
+  ctx->launches++;
+  LG_CUDA(ctx, cudaGetLastError());
+  return OK;
+}
+template <bool DIF>
+static int launch_global_pass_r(Ctx* ctx, int r, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s,
+                                const Fr* W) {
+  if (r == 3) return launch_global_pass<3, DIF>(ctx, in, out, copy_out, rows, q, s, W);
+  if (r == 2) return launch_global_pass<2, DIF>(ctx, in, out, copy_out, rows, q, s, W);
+  return launch_global_pass<1, DIF>(ctx, in, out, copy_out, rows, q, s, W);
+}
+
+template <int MODE>
+static int launch_local(Ctx* ctx, const LocalArgs& a) {
+  constexpr int E = 1 << kLogE;
+  const size_t smem = 4 * E * sizeof(uint4);
+  static bool configured[2] = {false, false};
+  if (!configured[MODE]) {
+    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_local_kernel<kLogE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    configured[MODE] = true;
+  }
+  const unsigned long long ctas = (a.total + E - 1) / E;
+  ntt_local_kernel<kLogE, MODE><<<(unsigned)ctas, E / 8, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  LG_CUDA(ctx, cudaGetLastError());
+  return OK;
+}
+
+int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* u) {
+  if (rows == 0) return OK;
+  if ((rows << log_k) >= ((size_t)1 << 42)) return set_error(ctx, ERR_INVALID, "matrix too large");
+  const NttTables* t;
+  LG_TRY(get_tables(ctx, log_k, rho_inv, &t));
+  const int q = log_k, l = q < kLogE ? q : kLogE;
+  const size_t total = rows << q;
+  LocalArgs a{};
+  a.out = u;
+  a.total = total;
+  a.plane_stride = total;
+  a.q = q;
+  a.l = l;
+  a.rho = rho_inv;
+  a.w_fwd = t->w_fwd;
+  a.w_inv = t->w_inv;
+  a.scale = t->scale;
+  if (q > l) {
+    void* tmp;
+    LG_TRY(ctx_scratch(ctx, total * sizeof(Fr), &tmp));
+    const Fr* src = msg;
+    bool first = true;
+    for (int top = q; top > l;) {
+      const int r = pass_radix(top - l), s = top - r;
+      LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, first ? u : nullptr, rows, q, s, t->w_inv));
+      src = (const Fr*)tmp;
+      first = false;
+      top = s;
+    }
+    a.in = (const Fr*)tmp;
+    a.copy_plane0 = 0;
+  } else {
+    a.in = msg;
+    a.copy_plane0 = 1;
+  }
+  LG_TRY(launch_local<0>(ctx, a));
+  if (q > l && rho_inv > 1) {
+    Fr* p = u + total;
+    for (int s = l; s < q;) {
+      const int r = pass_radix(q - s);
+      LG_TRY(launch_global_pass_r<false>(ctx, r, p, p, nullptr, rows * (size_t)(rho_inv - 1), q, s, t->w_fwd));
+      s += r;
+    }
+  }
+  return OK;
+}
+
+int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k) {
+  if (rows == 0) return OK;
+  const NttTables* t;
+  LG_TRY(get_tables(ctx, log_k, 1, &t));
+  const int q = log_k, l = q < kLogE ? q : kLogE;
+  const size_t total = rows << q;
+  LocalArgs a{};
+  a.out = out;
+  a.total = total;
+  a.plane_stride = total;
+  a.q = q;
+  a.l = l;
+  a.rho = 1;
+  a.w_fwd = t->w_fwd;
+  a.w_inv = t->w_inv;
+  a.scale = t->scale;
+  a.kinv = fr_inv(fr_from_u64((uint64_t)1 << q));
+  if (q > l) {
+    void* tmp;
+    LG_TRY(ctx_scratch(ctx, total * sizeof(Fr), &tmp));
+    const Fr* src = in;
+    for (int top = q; top > l;) {
+      const int r = pass_radix(top - l), s = top - r;
+      LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, nullptr, rows, q, s, t->w_inv));
+      src = (const Fr*)tmp;
+      top = s;
+    }
+    a.in = (const Fr*)tmp;
+  } else {
+    a.in = in;
+  }
+  return launch_local<1>(ctx, a);
+}
+
+}  // namespace lg

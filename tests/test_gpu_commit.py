@@ -1,0 +1,112 @@
+"""GPU parity: encode + column hash + Merkle root through the C ABI vs the Python oracle."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import ligero_oracle as O
+from ligero_b200 import fr_to_limbs, limbs_to_fr
+
+pytestmark = pytest.mark.gpu
+P = O.P
+
+
+def oracle_encode_commit(rows, k, rho):
+    dk, dn = O.Domain(k), O.Domain(rho * k)
+    u = [dn.fft(dk.ifft(r)) for r in rows]
+    n = rho * k
+    leaves = [O.column_hash([u[i][j] for i in range(len(rows))]) for j in range(n)]
+    tree = O.MerkleTree(leaves)
+    return u, leaves, tree
+
+
+def rand_matrix(rnd, R, k, zero_rows=()):
+    m = [[rnd.randrange(P) for _ in range(k)] for _ in range(R)]
+    for z in zero_rows:
+        m[z] = [0] * k
+    return m
+
+
+@pytest.mark.parametrize("R,k,rho", [
+    (1, 2, 8), (3, 4, 8), (16, 4, 8), (5, 8, 4), (7, 16, 8), (4, 32, 2), (9, 64, 8), (6, 128, 8),
+    (3, 256, 4), (5, 512, 8), (4, 1024, 8), (3, 2048, 8), (2, 4096, 4), (2, 8192, 8), (1, 16384, 4),
+])
+def test_encode_commit_matches_oracle(gpu_ctx, R, k, rho):
+    rnd = random.Random(R * 1000003 + k * 17 + rho)
+    zero_rows = (1,) if R > 2 else ()
+    msg = rand_matrix(rnd, R, k, zero_rows)
+    u, leaves, tree = oracle_encode_commit(msg, k, rho)
+    flat = fr_to_limbs([x for row in msg for x in row])
+    cm = gpu_ctx.commit(flat, R, k, rho)
+    try:
+        got = cm.read_rows(0, R)
+        for i in range(R):
+            assert limbs_to_fr(got[i]) == u[i], f"row {i} of U differs"
+        got_leaves = cm.read_leaves()
+        for j in range(rho * k):
+            assert bytes(got_leaves[j]) == leaves[j], f"leaf {j} differs"
+        nodes = cm.read_nodes()
+        assert [bytes(x) for x in nodes] == tree.nodes
+        assert cm.root == tree.root()
+    finally:
+        cm.free()
+
+
+def test_commit_device_input_and_recommit(gpu_ctx):
+    import torch
+    rnd = random.Random(7)
+    R, k, rho = 8, 64, 8
+    msg = rand_matrix(rnd, R, k)
+    _, _, tree = oracle_encode_commit(msg, k, rho)
+    flat = fr_to_limbs([x for row in msg for x in row])
+    dev = torch.from_numpy(flat.view(np.int64)).cuda()
+    cm = gpu_ctx.commit(dev, R, k, rho)
+    assert cm.root == tree.root()
+    msg2 = rand_matrix(rnd, R, k)
+    _, _, tree2 = oracle_encode_commit(msg2, k, rho)
+    assert cm.recommit(fr_to_limbs([x for row in msg2 for x in row])) == tree2.root()
+    cm.free()
+
+
+def test_format_switches(gpu_ctx):
+    rnd = random.Random(9)
+    R, k, rho = 5, 8, 8
+    msg = rand_matrix(rnd, R, k)
+    dk, dn = O.Domain(k), O.Domain(rho * k)
+    u = [dn.fft(dk.ifft(r)) for r in msg]
+    flat = fr_to_limbs([x for row in msg for x in row])
+    for col_p in (True, False):
+        for leaf_p in (True, False):
+            fmt = O.Formats(col_len_prefix=col_p, leaf_len_prefix=leaf_p)
+            leaves = [O.column_hash([u[i][j] for i in range(R)], O.FR, fmt) for j in range(rho * k)]
+            root = O.MerkleTree(leaves, fmt).root()
+            gpu_ctx.set_formats(col_p, leaf_p)
+            try:
+                cm = gpu_ctx.commit(flat, R, k, rho)
+                assert cm.root == root
+                cm.free()
+            finally:
+                gpu_ctx.set_formats(True, True)
+
+
+def test_intt_matches_oracle(gpu_ctx):
+    rnd = random.Random(11)
+    for rows, size in [(3, 2), (2, 16), (1, 1024), (2, 4096), (1, 32768)]:
+        ev = [[rnd.randrange(P) for _ in range(size)] for _ in range(rows)]
+        d = O.Domain(size)
+        want = [d.ifft(r) for r in ev]
+        got = gpu_ctx.intt(fr_to_limbs([x for r in ev for x in r]), rows, size)
+        got = limbs_to_fr(got)
+        for i in range(rows):
+            assert got[i * size:(i + 1) * size] == want[i]
+
+
+def test_invalid_arguments(gpu_ctx):
+    from ligero_b200 import LigeroB200Error
+    flat = fr_to_limbs([1, 2, 3])
+    with pytest.raises(LigeroB200Error):
+        gpu_ctx.commit(flat, 1, 3, 8)      # k not a power of two
+    with pytest.raises(LigeroB200Error):
+        gpu_ctx.commit(flat, 0, 2, 8)      # no rows
+    with pytest.raises(LigeroB200Error):
+        gpu_ctx.commit(flat, 1, 2, 3)      # rho_inv not a power of two
