@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Headline benchmark: Ligero prover encode+commit (Reed-Solomon row encoding + column hashing +
+Merkle tree) for the 2^24-gate synthetic-circuit witness matrix, in Fr elements/s encoded.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log-gates G]
+
+One "step" = one full encode+commit of the R x k pre-encoding matrix (R = 4m rows, k columns,
+n = 8k codeword length; shapes from src/ligero/mod.rs:171-175, 275-294 of the reference).
+  value : R*k*steps / device time, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the C ABI with HOST (pinned) input: H2D of the matrix and D2H of the
+          root inside the timed region
+Under torchrun (N > 1) the matrix is sharded across ranks (ligero_b200.parallel): rows for encoding,
+column ranges for hashing, one NVLink exchange in between, NCCL all-gather of subtree roots.
+`--impl reference` times the CPU restatement of the reference's own schedule (oracle/ligero_ref.c; the
+Rust reference cannot be built in this image) on a bounded row sample with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RHO_INV = 8
+METRIC = "fr_elems_per_s_encode_commit"
+UNIT = "Fr elems/s"
+
+
+def shape_for_gates(log_gates: int):
+    sol_len = (1 << log_gates) + 4                      # synthetic circuit, sol_len = G + 4
+    m = math.ceil(math.sqrt(float(sol_len)))
+    k = 1 << (m - 1).bit_length()
+    return 4 * m, k, RHO_INV * k, m
+
+
+def workload_name(log_gates, R, k, n):
+    return f"synthetic 2^{log_gates}-gate circuit witness matrix: {R}x{k} -> {R}x{n} (rho_inv=8), dense uniform Fr"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int = 0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def cpu_port_throughput(k: int, seconds_budget: float = 12.0, threads: int = 0):
+    """Time the CPU restatement (reference schedule) on a bounded row sample of the same workload."""
+    import numpy as np
+    from oracle import cref
+    threads = threads or os.cpu_count() or 1
+    rng = np.random.default_rng(2024)
+    rows = max(threads, 8)
+    total_rows, total_s = 0, 0.0
+    sample = None
+    for _ in range(4):
+        a = rng.integers(0, 2 ** 62, size=(rows * k, 4), dtype=np.uint64)
+        a[:, 3] &= (1 << 60) - 1
+        t0 = time.perf_counter()
+        cref.commit(a, rows, k, RHO_INV, threads=threads)
+        dt = time.perf_counter() - t0
+        sample = (rows, dt)
+        total_rows, total_s = rows, dt
+        if dt * 3 > seconds_budget:
+            break
+        rows = int(rows * min(4.0, max(1.5, seconds_budget / max(dt, 1e-3) / 2)))
+    return total_rows * k / total_s, total_rows, total_s, threads
+
+
+def run_reference(args):
+    """--impl reference: CPU restatement of the reference's schedule, all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    R, k, n, m = shape_for_gates(args.log_gates)
+    import numpy as np
+    from oracle import cref
+    threads = os.cpu_count() or 1
+    # size each step to ~ (120 s / steps) of CPU work using a short probe
+    tput, rows_p, secs_p, _ = cpu_port_throughput(k, seconds_budget=6.0, threads=threads)
+    per_row = secs_p / rows_p
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    rows = int(max(threads, min(R, budget / per_row)))
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 2 ** 62, size=(rows * k, 4), dtype=np.uint64)
+    a[:, 3] &= (1 << 60) - 1
+    for _ in range(args.warmup):
+        cref.commit(a, rows, k, RHO_INV, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cref.commit(a, rows, k, RHO_INV, threads=threads)
+    dt = time.perf_counter() - t0
+    value = rows * k * args.steps / dt
+    sample = f"{rows} of {R} rows x k={k} (n={n}) per step, {args.steps} steps, reference schedule (iFFT_k + zero-padded FFT_n per row, transpose, BLAKE2s per column, SHA-256 tree)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (R / rows), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 Montgomery (BN254 Fr)", "data": "synthetic",
+        "config": {"workload": workload_name(args.log_gates, R, k, n), "rows": R, "k": k, "n": n,
+                   "note": "ms_per_step is the sample time extrapolated linearly in rows to the full matrix"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-gates", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from ligero_b200 import Context
+    from ligero_b200.backend import _ptr, check
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    R, k, n, m = shape_for_gates(args.log_gates)
+    ctx = Context(local_rank)
+    peaks, peak_kind = measured_peaks()
+
+    if world > 1:
+        from ligero_b200.parallel import ShardedCommitter
+        result = ShardedCommitter.bench(ctx, R, k, RHO_INV, args, rank, world)
+        if rank == 0:
+            result["config"]["workload"] = workload_name(args.log_gates, R, k, n)
+            print(json.dumps(result))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
+    # ---------------- single GPU ----------------
+    g = torch.Generator(device="cuda")
+    g.manual_seed(20240 + rank)
+    msg = torch.randint(0, 2 ** 62, (R * k, 4), dtype=torch.int64, device="cuda", generator=g)
+    msg[:, 3] &= (1 << 60) - 1            # every element < r (top limb < 2^60)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    cm = ctx.commit(msg, R, k, RHO_INV)   # allocates U / leaves / tree once (not timed)
+    root0 = cm.root
+
+    def step_device():
+        check(ctx.lib.lg_recommit(cm.handle, _ptr(msg), None), ctx.handle, "lg_recommit")
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.sync()
+    int_peak = ctx.int_peak(60.0)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.set_timing(True)
+    ctx.phase_ms()
+    launches0 = ctx.launches
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    phases = ctx.phase_ms()
+    ctx.set_timing(False)
+    clocks = sampler.stop()
+    assert cm.hash() == root0, "root changed between steps"
+    ms_per_step = total_ms / args.steps
+    value = R * k / (ms_per_step * 1e-3)
+
+    # dominant kernel: the shared-memory NTT (iNTT tail + 7 coset NTTs): reads R*k, writes 7*R*k elements
+    local_ms, local_cnt = phases["ntt_local"]
+    local_ms_per_launch = local_ms / max(1, local_cnt)
+    local_bytes = 32.0 * R * k * RHO_INV
+    achieved_gbs = local_bytes / (local_ms_per_launch * 1e-3) / 1e9
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # integer roofline: Fr multiplications actually required by the encode schedule
+    logk = k.bit_length() - 1
+    w_mul = R * ((k // 2) * logk + (RHO_INV - 1) * ((k // 2) * logk + k))
+    enc_ms = sum(phases[p][0] for p in ("ntt_strided_inv", "ntt_local", "ntt_strided_fwd")) / args.steps
+    step_bytes = 32.0 * R * (k + 2 * n) + 64.0 * n
+    roofline = {
+        "bound": "hbm", "kernel": "ntt_local_kernel", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+        "note": "multi-limb modular arithmetic is integer-pipe bound, not HBM bound (north_star): see int_roofline",
+        "int_roofline": {
+            "bound": "int (IMAD.WIDE.U32 via Montgomery multiplications)",
+            "fr_mul_required_per_step": w_mul,
+            "achieved_fr_mul_per_s": w_mul / (enc_ms * 1e-3),
+            "peak_fr_mul_per_s": int_peak["fr_mul_per_s"],
+            "frac": (w_mul / (enc_ms * 1e-3)) / int_peak["fr_mul_per_s"],
+            "peak_source": "lg_bench_int_peak: dependent Montgomery-multiply chains at 2048 threads/SM, measured in this run",
+            "encode_ms_per_step": enc_ms,
+        },
+        "step_hbm": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9},
+        "phase_ms_per_step": {p: v[0] / args.steps for p, v in phases.items() if v[1]},
+    }
+
+    # ---------------- end to end: host (pinned) matrix -> root on host ----------------
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((R * k, 4), dtype=torch.int64, pin_memory=True)
+        host.copy_(msg)
+        root_host = np.zeros(32, dtype=np.uint8)
+        for _ in range(2):
+            check(ctx.lib.lg_recommit(cm.handle, _ptr(host), _ptr(root_host)), ctx.handle, "lg_recommit(host)")
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            check(ctx.lib.lg_recommit(cm.handle, _ptr(host), _ptr(root_host)), ctx.handle, "lg_recommit(host)")
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        e2e_ms = max(e0.elapsed_time(e1), wall * 1e3) / args.steps
+        assert bytes(root_host) == root0
+        e2e = {"value": R * k / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": R * k * 32, "d2h_bytes_per_step": 32,
+               "ms_per_step": e2e_ms, "api": "lg_recommit(host pinned matrix) -> root on host"}
+        del host
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        v, rows_s, secs, thr = cpu_port_throughput(k)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
+                        "sample": f"{rows_s} of {R} rows x k={k} (n={n}), reference schedule, {secs:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32x8 Montgomery (BN254 Fr)", "data": "synthetic",
+        "config": {"workload": workload_name(args.log_gates, R, k, n), "rows": R, "k": k, "n": n, "rho_inv": RHO_INV,
+                   "l2_policy": "inputs larger than L2 (4 GiB matrix, 32 GiB codeword matrix per step)",
+                   "codeword_elems_per_s": value * RHO_INV},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,20 @@ uint64_t lg_ctx_launches(const lg_ctx* ctx);
 int lg_ctx_set_formats(lg_ctx* ctx, int col_len_prefix, int leaf_len_prefix);
 /* the stream the context launches on, as a cudaStream_t (for CUDA-event timing by the caller) */
 void* lg_ctx_stream(const lg_ctx* ctx);
+/* per-phase device timing: when enabled, every phase boundary records a CUDA event on the context
+ * stream; lg_ctx_phase_ms synchronises, writes the accumulated milliseconds and interval counts per
+ * phase (LG_PHASE_*) since the last query, and resets.  n = number of entries in the output arrays. */
+#define LG_PHASE_NTT_STRIDED_INV 0 /* register-only DIF passes over HBM (rows longer than one CTA tile) */
+#define LG_PHASE_NTT_LOCAL 1       /* shared-memory iNTT tail + all coset NTTs */
+#define LG_PHASE_NTT_STRIDED_FWD 2 /* register-only DIT passes over HBM */
+#define LG_PHASE_HASH 3            /* BLAKE2s column hashing */
+#define LG_PHASE_MERKLE 4          /* SHA-256 tree */
+#define LG_PHASE_EXPAND 5          /* ChaCha20 challenge expansion */
+#define LG_PHASE_TESTS 6           /* row combination / linear / quadratic tests */
+#define LG_PHASE_OPEN 7            /* column gather */
+#define LG_PHASE_COUNT 8
+int lg_ctx_set_timing(lg_ctx* ctx, int enabled);
+int lg_ctx_phase_ms(lg_ctx* ctx, double* ms_out, uint64_t* count_out, int n);
 
 /* ---- encode + commit: replaces src/ligero/mod.rs:521-551 ------------------------------------ */
 /* (reed_solomon_interpolate 998-1002, reed_solomon_evaluate 1004-1008 per row; DenseMatrix::columns

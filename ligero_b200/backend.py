@@ -91,6 +91,19 @@ class Context:
     def stream(self) -> int:
         return int(self.lib.lg_ctx_stream(self.handle) or 0)
 
+    PHASES = ("ntt_strided_inv", "ntt_local", "ntt_strided_fwd", "hash", "merkle", "expand", "tests", "open")
+
+    def set_timing(self, enabled: bool = True):
+        check(self.lib.lg_ctx_set_timing(self.handle, int(enabled)), self.handle)
+
+    def phase_ms(self):
+        """{phase: (accumulated ms, intervals)} since the last call (synchronises the stream)."""
+        n = len(self.PHASES)
+        ms = (c_double * n)()
+        cnt = (ctypes.c_uint64 * n)()
+        check(self.lib.lg_ctx_phase_ms(self.handle, ms, cnt, n), self.handle)
+        return {p: (ms[i], int(cnt[i])) for i, p in enumerate(self.PHASES)}
+
     def set_formats(self, col_len_prefix: bool = True, leaf_len_prefix: bool = True):
         check(self.lib.lg_ctx_set_formats(self.handle, int(col_len_prefix), int(leaf_len_prefix)), self.handle)
 

@@ -24,6 +24,19 @@ int set_error(Ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
+void phase_mark(Ctx* ctx, int phase_ended) {
+  if (!ctx->timing) return;
+  cudaEvent_t e;
+  if (!ctx->event_pool.empty()) {
+    e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+  } else if (cudaEventCreate(&e) != cudaSuccess) {
+    return;
+  }
+  cudaEventRecord(e, ctx->stream);
+  ctx->marks.emplace_back(phase_ended, e);
+}
+
 int ctx_scratch(Ctx* ctx, size_t bytes, void** out) {
   if (bytes > ctx->scratch_bytes) {
     if (ctx->scratch) {
@@ -172,8 +185,11 @@ static int do_encode(lg_matrix* h, const uint64_t* preenc_u) {
 static int do_hash(lg_matrix* h, uint8_t root_out[32]) {
   Matrix& m = h->m;
   Ctx* c = m.ctx;
+  phase_mark(c, PH_BEGIN);
   LG_TRY(hash_columns(c, m.u, m.rows, m.log_k, m.rho_inv, m.leaves, h->owner->col_len_prefix));
+  phase_mark(c, PH_HASH);
   LG_TRY(merkle_build(c, m.leaves, m.n, m.nodes, h->owner->leaf_len_prefix));
+  phase_mark(c, PH_MERKLE);
   if (root_out) {
     LG_CUDA(c, cudaMemcpyAsync(root_out, m.nodes, 32, cudaMemcpyDeviceToHost, c->stream));
     LG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -220,6 +236,8 @@ int lg_ctx_destroy(lg_ctx* ctx) {
     cudaFree(kv.second.scale);
   }
   if (ctx->c.scratch) cudaFree(ctx->c.scratch);
+  for (auto& m : ctx->c.marks) cudaEventDestroy(m.second);
+  for (auto& e : ctx->c.event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
   return OK;
@@ -243,6 +261,34 @@ int lg_ctx_set_formats(lg_ctx* ctx, int col_len_prefix, int leaf_len_prefix) {
 }
 
 void* lg_ctx_stream(const lg_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+
+int lg_ctx_set_timing(lg_ctx* ctx, int enabled) {
+  if (!ctx) return ERR_INVALID;
+  ctx->c.timing = enabled != 0;
+  return OK;
+}
+
+int lg_ctx_phase_ms(lg_ctx* ctx, double* ms_out, uint64_t* count_out, int n) {
+  if (!ctx) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; i++) {
+    if (ms_out) ms_out[i] = 0;
+    if (count_out) count_out[i] = 0;
+  }
+  for (size_t i = 1; i < c->marks.size(); i++) {
+    const int ph = c->marks[i].first;
+    if (ph < 0 || ph >= n) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->marks[i - 1].second, c->marks[i].second) == cudaSuccess) {
+      if (ms_out) ms_out[ph] += ms;
+      if (count_out) count_out[ph] += 1;
+    }
+  }
+  for (auto& m : c->marks) c->event_pool.push_back(m.second);
+  c->marks.clear();
+  return OK;
+}
 
 int lg_encode(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out) {
   if (!ctx) return ERR_INVALID;

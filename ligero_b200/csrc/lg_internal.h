@@ -56,7 +56,16 @@ struct Ctx {
   // scratch reused across calls
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // optional per-phase device timing (CUDA events on `stream`): bench.py's live kernel durations
+  bool timing = false;
+  std::vector<std::pair<int, cudaEvent_t>> marks;  // (phase that ENDS at this event, event)
+  std::vector<cudaEvent_t> event_pool;
 };
+
+// phases reported by lg_ctx_phase_ms
+enum Phase : int { PH_BEGIN = -1, PH_NTT_STRIDED_INV = 0, PH_NTT_LOCAL = 1, PH_NTT_STRIDED_FWD = 2, PH_HASH = 3, PH_MERKLE = 4,
+                   PH_EXPAND = 5, PH_TESTS = 6, PH_OPEN = 7, PH_COUNT = 8 };
+void phase_mark(Ctx* ctx, int phase_ended);
 
 int ctx_scratch(Ctx* ctx, size_t bytes, void** out);
 int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out);
@@ -87,5 +96,7 @@ int hash_columns(Ctx* ctx, const Fr* u_planes, size_t rows, int log_k, int rho_i
                  bool len_prefix);
 // Merkle tree (a6)
 int merkle_build(Ctx* ctx, const uint8_t* leaves, size_t n, uint8_t* nodes, bool leaf_len_prefix);
+// BLAKE2s of `count` explicit columns (each `rows` contiguous Montgomery elements)
+int hash_column_list(Ctx* ctx, const Fr* cols, size_t rows, size_t count, uint8_t* digests, bool len_prefix);
 
 }  // namespace lg

@@ -11,6 +11,8 @@
 // stages from register-only radix-2/4/8 passes over global memory (fully coalesced: consecutive threads
 // touch consecutive 32-byte elements).  All-zero rows (about half of the witness matrix) are
 // detected at load time and short-circuited to zero stores.
+#include <cstdlib>
+
 #include "fr_host.h"
 #include "lg_internal.h"
 
@@ -121,17 +123,20 @@ __device__ __forceinline__ void smem_pass(const uint4* slo, const uint4* shi, ui
   }
 }
 
-template <bool DIF, bool SCALE>
+template <int MAXR, bool DIF, bool SCALE>
 __device__ __forceinline__ void smem_pass_r(int r, const uint4* slo, const uint4* shi, uint4* dlo, uint4* dhi, int s,
                                             int q, const Fr* W, const Fr* scale, uint32_t col_base, uint32_t col_mask,
                                             int E, int NT) {
-  if (r == 3) smem_pass<3, DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
+  if (MAXR >= 3 && r == 3) smem_pass<(MAXR >= 3 ? 3 : 2), DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
   else if (r == 2) smem_pass<2, DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
   else smem_pass<1, DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
 }
 
 // stage grouping: radix 8 wherever possible, never a lone radix-2 after radix-8 when 4 stages remain
-__host__ __device__ __forceinline__ int pass_radix(int remaining) { return remaining == 4 ? 2 : (remaining < 3 ? remaining : 3); }
+__host__ __device__ __forceinline__ int pass_radix(int remaining, int maxr = 3) {
+  if (maxr == 2) return remaining < 2 ? remaining : 2;
+  return remaining == 4 ? 2 : (remaining < 3 ? remaining : 3);
+}
 
 struct LocalArgs {
   const Fr* in;         // rows*k elements (message, or output of the strided DIF passes)
@@ -142,16 +147,16 @@ struct LocalArgs {
   int l;                // local stages = min(q, LOG_E)
   int rho;              // cosets (MODE 0)
   int copy_plane0;      // MODE 0: also store the input to plane 0 (only when `in` is the message)
-  const Fr* w_fwd;
+  const Fr* w_fwd;      // order-2^l tables (compact: every local stage indexes a dense 2^(l-1)-entry array)
   const Fr* w_inv;
   const Fr* scale;
   Fr kinv;              // MODE 1: 1/k
 };
 
 // MODE 0: encode (iNTT tail + all cosets).  MODE 1: iNTT tail only, scaled, natural-order output.
-template <int LOG_E, int MODE>
-__global__ void __launch_bounds__(1 << (LOG_E - 3)) ntt_local_kernel(const LocalArgs a) {
-  constexpr int E = 1 << LOG_E, NT = E / 8;
+template <int LOG_E, int MAXR, int MINB, int MODE>
+__global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(const LocalArgs a) {
+  constexpr int E = 1 << LOG_E, NT = E >> MAXR;
   extern __shared__ uint4 smem[];
   uint4 *Alo = smem, *Ahi = smem + E, *Blo = smem + 2 * E, *Bhi = smem + 3 * E;
   const unsigned long long f0 = (unsigned long long)blockIdx.x * E;
@@ -183,8 +188,8 @@ __global__ void __launch_bounds__(1 << (LOG_E - 3)) ntt_local_kernel(const Local
 
   // inverse transform tail: DIF stages l-1 .. 0 in place in A
   for (int top = a.l; top > 0;) {
-    const int r = pass_radix(top), s = top - r;
-    smem_pass_r<true, false>(r, Alo, Ahi, Alo, Ahi, s, a.q, a.w_inv, nullptr, 0, 0, E, NT);
+    const int r = pass_radix(top, MAXR), s = top - r;
+    smem_pass_r<MAXR, true, false>(r, Alo, Ahi, Alo, Ahi, s, a.l, a.w_inv, nullptr, 0, 0, E, NT);
     __syncthreads();
     top = s;
   }
@@ -205,9 +210,9 @@ __global__ void __launch_bounds__(1 << (LOG_E - 3)) ntt_local_kernel(const Local
   for (int cs = 1; cs < a.rho; cs++) {
     const Fr* sc = a.scale + (size_t)(cs - 1) * ((size_t)1 << a.q);
     for (int s = 0; s < a.l;) {
-      const int r = pass_radix(a.l - s);
-      if (s == 0) smem_pass_r<false, true>(r, Alo, Ahi, Blo, Bhi, 0, a.q, a.w_fwd, sc, col_base, col_mask, E, NT);
-      else smem_pass_r<false, false>(r, Blo, Bhi, Blo, Bhi, s, a.q, a.w_fwd, nullptr, 0, 0, E, NT);
+      const int r = pass_radix(a.l - s, MAXR);
+      if (s == 0) smem_pass_r<MAXR, false, true>(r, Alo, Ahi, Blo, Bhi, 0, a.l, a.w_fwd, sc, col_base, col_mask, E, NT);
+      else smem_pass_r<MAXR, false, false>(r, Blo, Bhi, Blo, Bhi, s, a.l, a.w_fwd, nullptr, 0, 0, E, NT);
       __syncthreads();
       s += r;
     }
@@ -299,7 +304,9 @@ int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out) {
   return OK;
 }
 
-constexpr int kLogE = 10;  // 1024 elements / CTA: 64 KiB of shared memory, 128 threads, 3 CTAs per SM
+constexpr int kLogE = 10;  // 1024 elements / CTA = 64 KiB of shared memory
+constexpr int kMaxR = 2;   // radix-4 passes: 256 threads x 4 elements, <= 85 registers -> 3 CTAs = 24 warps per SM
+constexpr int kMinB = 3;   // (measured best of the four variants below: 131 ms vs 138/164/158 ms at 16388 x 8192)
 
 template <int R, bool DIF>
 static int launch_global_pass(Ctx* ctx, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s, const Fr* W) {
@@ -319,21 +326,44 @@ static int launch_global_pass_r(Ctx* ctx, int r, const Fr* in, Fr* out, Fr* copy
   return launch_global_pass<1, DIF>(ctx, in, out, copy_out, rows, q, s, W);
 }
 
-template <int MODE>
-static int launch_local(Ctx* ctx, const LocalArgs& a) {
+template <int MAXR, int MINB, int MODE>
+static int launch_local_v(Ctx* ctx, const LocalArgs& a) {
   constexpr int E = 1 << kLogE;
   const size_t smem = 4 * E * sizeof(uint4);
-  static bool configured[2] = {false, false};
-  if (!configured[MODE]) {
-    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_local_kernel<kLogE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)smem));
-    configured[MODE] = true;
+  static bool configured = false;
+  if (!configured) {
+    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_local_kernel<kLogE, MAXR, MINB, MODE>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
   }
   const unsigned long long ctas = (a.total + E - 1) / E;
-  ntt_local_kernel<kLogE, MODE><<<(unsigned)ctas, E / 8, smem, ctx->stream>>>(a);
+  ntt_local_kernel<kLogE, MAXR, MINB, MODE><<<(unsigned)ctas, E >> MAXR, smem, ctx->stream>>>(a);
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
+}
+
+// LG_NTT_VARIANT selects alternative register/occupancy trade-offs of the same kernel (tuning hook)
+static int ntt_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LG_NTT_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+template <int MODE>
+static int launch_local(Ctx* ctx, const LocalArgs& a) {
+  if (MODE == 0) {
+    switch (ntt_variant()) {
+      case 1: return launch_local_v<2, 2, MODE>(ctx, a);   // radix-4, 2 CTAs/SM (<= 128 regs)
+      case 2: return launch_local_v<3, 3, MODE>(ctx, a);   // radix-8, 128 threads, 3 CTAs/SM (<= 168 regs)
+      case 3: return launch_local_v<3, 2, MODE>(ctx, a);   // radix-8, 128 threads, 2 CTAs/SM
+      default: break;
+    }
+  }
+  return launch_local_v<kMaxR, kMinB, MODE>(ctx, a);
 }
 
 int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* u) {
@@ -342,6 +372,8 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
   const NttTables* t;
   LG_TRY(get_tables(ctx, log_k, rho_inv, &t));
   const int q = log_k, l = q < kLogE ? q : kLogE;
+  const NttTables* tl = t;
+  if (l != q) LG_TRY(get_tables(ctx, l, 1, &tl));
   const size_t total = rows << q;
   LocalArgs a{};
   a.out = u;
@@ -350,9 +382,10 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
   a.q = q;
   a.l = l;
   a.rho = rho_inv;
-  a.w_fwd = t->w_fwd;
-  a.w_inv = t->w_inv;
+  a.w_fwd = tl->w_fwd;
+  a.w_inv = tl->w_inv;
   a.scale = t->scale;
+  phase_mark(ctx, PH_BEGIN);
   if (q > l) {
     void* tmp;
     LG_TRY(ctx_scratch(ctx, total * sizeof(Fr), &tmp));
@@ -367,11 +400,13 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
     }
     a.in = (const Fr*)tmp;
     a.copy_plane0 = 0;
+    phase_mark(ctx, PH_NTT_STRIDED_INV);
   } else {
     a.in = msg;
     a.copy_plane0 = 1;
   }
   LG_TRY(launch_local<0>(ctx, a));
+  phase_mark(ctx, PH_NTT_LOCAL);
   if (q > l && rho_inv > 1) {
     Fr* p = u + total;
     for (int s = l; s < q;) {
@@ -379,6 +414,7 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
       LG_TRY(launch_global_pass_r<false>(ctx, r, p, p, nullptr, rows * (size_t)(rho_inv - 1), q, s, t->w_fwd));
       s += r;
     }
+    phase_mark(ctx, PH_NTT_STRIDED_FWD);
   }
   return OK;
 }
@@ -388,6 +424,8 @@ int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k) {
   const NttTables* t;
   LG_TRY(get_tables(ctx, log_k, 1, &t));
   const int q = log_k, l = q < kLogE ? q : kLogE;
+  const NttTables* tl = t;
+  if (l != q) LG_TRY(get_tables(ctx, l, 1, &tl));
   const size_t total = rows << q;
   LocalArgs a{};
   a.out = out;
@@ -396,8 +434,8 @@ int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k) {
   a.q = q;
   a.l = l;
   a.rho = 1;
-  a.w_fwd = t->w_fwd;
-  a.w_inv = t->w_inv;
+  a.w_fwd = tl->w_fwd;
+  a.w_inv = tl->w_inv;
   a.scale = t->scale;
   a.kinv = fr_inv(fr_from_u64((uint64_t)1 << q));
   if (q > l) {

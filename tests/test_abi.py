@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/ligero_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "ligero_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ligero_b200 import build
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    syms = declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/ligero_b200.h but not exported"
+
+
+def test_python_binding_covers_header():
+    from ligero_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    _lib.load()
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without CUDA devices, creating a context must fail loudly."""
+    import torch
+    from ligero_b200 import Context, LigeroB200Error
+    if torch.cuda.is_available():
+        return
+    try:
+        Context(0)
+    except LigeroB200Error as e:
+        assert "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("Context(0) succeeded without a GPU")
+
+
+def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under ligero_b200/ may import, link or execute it."""
+    pkg = os.path.join(ROOT, "ligero_b200")
+    pat = re.compile(r"(from\s+oracle|import\s+oracle|oracle/|ligero_ref|cref)")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(text), f"{os.path.join(dirpath, f)} references the oracle"
