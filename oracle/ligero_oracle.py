@@ -855,6 +855,8 @@ class LigeroCircuit:
         neg1 = p - 1
 
         def add_row(l, r, own_col):
+            if nodes[l][0] == CONST and nodes[r][0] == CONST:
+                raise ValueError("Add(constant, constant) is not supported (the reference panics, mod.rs:325)")
             if nodes[l][0] == CONST:
                 row = [(nodes[l][1], 0), (1, index_map[r])]
             elif nodes[r][0] == CONST:
@@ -865,6 +867,9 @@ class LigeroCircuit:
             return row
 
         def mul_rows(l, r):
+            if nodes[l][0] == CONST and nodes[r][0] == CONST:
+                # the reference hits `index_map.get(r_node).unwrap()` on None here (mod.rs:345; TODO at 148-150)
+                raise ValueError("Mul(constant, constant) is not supported (the reference panics)")
             if nodes[l][0] == CONST:
                 return [(nodes[l][1], 0)], [(1, index_map[r])]
             if nodes[r][0] == CONST:

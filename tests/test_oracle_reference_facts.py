@@ -126,10 +126,17 @@ def test_circom_fixtures():
     assert circ.num_nodes() == 15
     tr = circ.evaluation_trace_multioutput([(1, 3), (2, 9)], outs)
     assert [tr[o] for o in outs] == [1, 1]
+    # cube compiles to a Mul(27, -1) gate (constant x constant): LigeroCircuit::new panics in the reference
+    # (index_map.get(..).unwrap() on a constant, src/ligero/mod.rs:345), so the mirror must refuse it too
+    with pytest.raises(ValueError):
+        O.LigeroCircuit(circ, outs)
+    # multiplication has no such gate: full prove/verify
+    a, b, c, nw = O.read_r1cs(f"{REF}/circom/multiplication.r1cs")
+    circ, outs = O.ArithmeticCircuit.from_constraint_system(a, b, c, nw)
     lc = O.LigeroCircuit(circ, outs)
     assert (lc.m, lc.k, lc.n, lc.t) == (4, 4, 32, 32)
-    assert lc.verify(lc.prove([(1, 3), (2, 9)], sponge()), sponge())
-    assert not lc.verify(lc.prove([(1, 3), (2, 10)], sponge()), sponge())
+    assert lc.verify(lc.prove([(1, 6), (2, 3), (3, 2)], sponge()), sponge())
+    assert not lc.verify(lc.prove([(1, 7), (2, 3), (3, 2)], sponge()), sponge())
 
 
 @pytest.mark.skipif(not have_ref, reason="reference fixtures not mounted")
