@@ -91,6 +91,44 @@ int lg_matrix_read_nodes(const lg_matrix* m, uint8_t* out /* (n-1)*32, heap orde
 /* in/out : Fr[rows * size], natural order, includes 1/size; host or device, may alias */
 int lg_intt(lg_ctx* ctx, const uint64_t* in, uint64_t* out, size_t rows, size_t size);
 
+/* ---- challenge expansion: replaces src/utils.rs:23-55 --------------------------------------- */
+/* get_field_elements_from_prng(count, seed): ChaCha20Rng(seed) -> F::rand x count, rejection sampled;
+ * the accepted 254-bit integer is used as the Montgomery representation.  out: Fr[count], host or device. */
+int lg_expand_fr(lg_ctx* ctx, const uint8_t seed[32], size_t count, uint64_t* out);
+/* get_distinct_indices_from_prng(n, t, seed): t ascending distinct indices in [0, n) (host, tiny) */
+int lg_expand_indices(const uint8_t seed[32], size_t n, size_t t, uint64_t* idx_out);
+
+/* ---- Test-Interleaved: DenseMatrix::row_mul, src/matrices/mod.rs:138-149 (call mod.rs:658) ---- */
+/* out[c] = sum_i r[i] * U_pre[i][c];  r: Fr[rows] (host or device), out: Fr[k] (host) */
+int lg_row_combine(lg_matrix* m, const uint64_t* r, uint64_t* out);
+
+/* ---- constraint matrix A = [[I, -(Px;Py;Pz)], [0, Padd]]  (src/ligero/mod.rs:296-433) ---------- */
+/* Only the right-hand block (4mk rows x mk columns) is uploaded, in CSC form: column c holds entries
+ * [col_ptr[c], col_ptr[c+1]) with row index row_idx[e] in [0, 4mk) and value id val_id[e]:
+ * 0 -> +1, 1 -> -1, v >= 2 -> const_table[v - 2] (Fr).  One upload per circuit. */
+typedef struct lg_constraints lg_constraints;
+int lg_constraints_create(lg_ctx* ctx, size_t mk, const uint32_t* col_ptr, const uint32_t* row_idx, const uint32_t* val_id,
+                          size_t nnz, const uint64_t* const_table, size_t n_consts, lg_constraints** out);
+int lg_constraints_free(lg_constraints* a);
+/* SparseMatrix::row_mul, src/matrices/mod.rs:100-110 (call mod.rs:722): out = r^T A, Fr[4mk] each */
+int lg_sparse_row_mul(lg_ctx* ctx, const lg_constraints* a, const uint64_t* r_linear, uint64_t* out);
+
+/* ---- Test-Linear-Constraints polynomial: src/ligero/mod.rs:719-736 ----------------------------- */
+/* q = sum_i p_i * r_i with r_i = ifft_k(rows of r^T A); coeffs_out: Fr[2k] capacity (host), *len_out =
+ * number of coefficients after stripping trailing zeros (DensePolynomial semantics).  The seeded form
+ * expands r_linear = get_field_elements_from_prng(4mk, seed) on the device. */
+int lg_linear_test(lg_matrix* m, const lg_constraints* a, const uint64_t* r_linear, uint64_t* coeffs_out, size_t* len_out);
+int lg_linear_test_seeded(lg_matrix* m, const lg_constraints* a, const uint8_t seed[32], uint64_t* coeffs_out, size_t* len_out);
+
+/* ---- Test-Quadratic-Constraints polynomial: src/ligero/mod.rs:839-848 -------------------------- */
+/* q = sum_{i<m} r[i] (p_x,i p_y,i - p_z,i);  r_quad: Fr[m] */
+int lg_quadratic_test(lg_matrix* m, const uint64_t* r_quad, uint64_t* coeffs_out, size_t* len_out);
+
+/* ---- openings: src/ligero/mod.rs:935-955 (DenseMatrix::column + MerkleTree::generate_proof) ---- */
+/* cols_out: Fr[t*rows] (column q = U[:, idx[q]]);  sib_out: t*32 bytes (leaf_sibling_hash);
+ * auth_out: t*(log2(n)-1)*32 bytes, per column the sibling digests from just below the root downwards */
+int lg_open(lg_matrix* m, const uint64_t* idx, size_t t, uint64_t* cols_out, uint8_t* sib_out, uint8_t* auth_out);
+
 /* ---- measured integer roofline ----------------------------------------------------------------- */
 /* Runs dependent-chain microbenchmarks at full occupancy for ~`ms_target` milliseconds each and
  * reports sustained Montgomery multiplications/s and IMAD.WIDE.U32 (32x32+64) operations/s. */

@@ -5,4 +5,4 @@ the host-side mirror used by tests and benchmarks.  There is no CPU fallback: cr
 without the built library or without a GPU raises LigeroB200Error.
 """
 from ._lib import LIB_PATH, LigeroB200Error  # noqa: F401
-from .backend import BN254_R, CommittedMatrix, Context, fr_to_limbs, limbs_to_fr  # noqa: F401
+from .backend import BN254_R, CommittedMatrix, Constraints, Context, fr_to_limbs, limbs_to_fr  # noqa: F401

@@ -41,6 +41,17 @@ SIGNATURES = {
     "lg_matrix_read_rows": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "lg_matrix_read_leaves": (c_int, [c_void_p, c_void_p]),
     "lg_matrix_read_nodes": (c_int, [c_void_p, c_void_p]),
+    "lg_expand_fr": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lg_expand_indices": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
+    "lg_row_combine": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lg_constraints_create": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
+                                      POINTER(c_void_p)]),
+    "lg_constraints_free": (c_int, [c_void_p]),
+    "lg_sparse_row_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lg_linear_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_size_t)]),
+    "lg_linear_test_seeded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_size_t)]),
+    "lg_quadratic_test": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_size_t)]),
+    "lg_open": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "lg_intt": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t]),
     "lg_bench_int_peak": (c_int, [c_void_p, c_double, POINTER(c_double), POINTER(c_double)]),
 }

@@ -127,10 +127,63 @@ class Context:
         check(self.lib.lg_intt(self.handle, _ptr(evals), _ptr(out), rows, size), self.handle, "lg_intt")
         return out
 
+    # ---- challenges ------------------------------------------------------------------------
+    def expand_fr(self, seed: bytes, count: int, out=None):
+        """get_field_elements_from_prng on the device; returns uint64[count,4] (host) unless `out` given."""
+        assert len(seed) == 32
+        if out is None:
+            out = np.empty((count, 4), dtype=np.uint64)
+        s = np.frombuffer(seed, dtype=np.uint8).copy()
+        check(self.lib.lg_expand_fr(self.handle, _ptr(s), count, _ptr(out)), self.handle, "lg_expand_fr")
+        return out
+
+    def expand_indices(self, seed: bytes, n: int, t: int) -> np.ndarray:
+        assert len(seed) == 32
+        out = np.empty(t, dtype=np.uint64)
+        s = np.frombuffer(seed, dtype=np.uint8).copy()
+        check(self.lib.lg_expand_indices(_ptr(s), n, t, _ptr(out)), self.handle, "lg_expand_indices")
+        return out
+
+    def constraints(self, mk: int, col_ptr, row_idx, val_id, const_table=None) -> "Constraints":
+        return Constraints(self, mk, col_ptr, row_idx, val_id, const_table)
+
     def int_peak(self, ms_target: float = 50.0):
         a, b = c_double(), c_double()
         check(self.lib.lg_bench_int_peak(self.handle, ms_target, byref(a), byref(b)), self.handle, "lg_bench_int_peak")
         return {"fr_mul_per_s": a.value, "imad_wide_per_s": b.value}
+
+
+class Constraints:
+    """lg_constraints: CSC of the right-hand block of A on the device."""
+
+    def __init__(self, ctx: Context, mk: int, col_ptr, row_idx, val_id, const_table=None):
+        self.ctx, self.mk = ctx, mk
+        cp = np.ascontiguousarray(col_ptr, dtype=np.uint32)
+        ri = np.ascontiguousarray(row_idx, dtype=np.uint32)
+        vi = np.ascontiguousarray(val_id, dtype=np.uint32)
+        ct = np.ascontiguousarray(const_table, dtype=np.uint64).reshape(-1, 4) if const_table is not None else np.zeros((0, 4), np.uint64)
+        h = c_void_p()
+        check(ctx.lib.lg_constraints_create(ctx.handle, mk, _ptr(cp), _ptr(ri) if len(ri) else None, _ptr(vi) if len(vi) else None,
+                                            len(ri), _ptr(ct) if len(ct) else None, len(ct), byref(h)),
+              ctx.handle, "lg_constraints_create")
+        self.handle = h
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.lg_constraints_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def row_mul(self, r_linear) -> np.ndarray:
+        out = np.empty((4 * self.mk, 4), dtype=np.uint64)
+        check(self.ctx.lib.lg_sparse_row_mul(self.ctx.handle, self.handle, _ptr(r_linear), _ptr(out)), self.ctx.handle,
+              "lg_sparse_row_mul")
+        return out
 
 
 class CommittedMatrix:
@@ -164,6 +217,41 @@ class CommittedMatrix:
         check(self.ctx.lib.lg_matrix_hash(self.handle, _ptr(root)), self.ctx.handle, "lg_matrix_hash")
         self.root = bytes(root)
         return self.root
+
+    # ---- tests and openings ----------------------------------------------------------------
+    def row_combine(self, r) -> np.ndarray:
+        out = np.empty((self.k, 4), dtype=np.uint64)
+        check(self.ctx.lib.lg_row_combine(self.handle, _ptr(r), _ptr(out)), self.ctx.handle, "lg_row_combine")
+        return out
+
+    def linear_test(self, constraints: "Constraints", r_linear=None, seed: Optional[bytes] = None) -> np.ndarray:
+        out = np.empty((2 * self.k, 4), dtype=np.uint64)
+        ln = c_size_t()
+        if seed is not None:
+            s = np.frombuffer(seed, dtype=np.uint8).copy()
+            st = self.ctx.lib.lg_linear_test_seeded(self.handle, constraints.handle, _ptr(s), _ptr(out), byref(ln))
+        else:
+            st = self.ctx.lib.lg_linear_test(self.handle, constraints.handle, _ptr(r_linear), _ptr(out), byref(ln))
+        check(st, self.ctx.handle, "lg_linear_test")
+        return out[: ln.value]
+
+    def quadratic_test(self, r_quad) -> np.ndarray:
+        out = np.empty((2 * self.k, 4), dtype=np.uint64)
+        ln = c_size_t()
+        check(self.ctx.lib.lg_quadratic_test(self.handle, _ptr(r_quad), _ptr(out), byref(ln)), self.ctx.handle, "lg_quadratic_test")
+        return out[: ln.value]
+
+    def open(self, idx):
+        """(columns uint64[t, rows, 4], leaf_sibling uint8[t,32], auth uint8[t, log2(n)-1, 32])"""
+        ii = np.ascontiguousarray(idx, dtype=np.uint64)
+        t = len(ii)
+        depth = self.n.bit_length() - 2
+        cols = np.empty((t, self.rows, 4), dtype=np.uint64)
+        sib = np.empty((t, 32), dtype=np.uint8)
+        auth = np.empty((t, max(depth, 0), 32), dtype=np.uint8)
+        check(self.ctx.lib.lg_open(self.handle, _ptr(ii), t, _ptr(cols), _ptr(sib), _ptr(auth) if depth > 0 else None),
+              self.ctx.handle, "lg_open")
+        return cols, sib, auth
 
     def read_rows(self, row0: int, nrows: int) -> np.ndarray:
         out = np.empty((nrows, self.n, 4), dtype=np.uint64)

@@ -7,15 +7,7 @@
 #include "fr_host.h"
 #include "lg_internal.h"
 
-struct lg_ctx {
-  lg::Ctx c;
-  bool col_len_prefix = true;
-  bool leaf_len_prefix = true;
-};
-struct lg_matrix {
-  lg::Matrix m;
-  lg_ctx* owner = nullptr;
-};
+#include "capi_types.h"
 
 namespace lg {
 
@@ -54,7 +46,7 @@ int ctx_scratch(Ctx* ctx, size_t bytes, void** out) {
 }
 
 // true if p is device (or managed) memory
-static bool is_device_ptr(const void* p) {
+bool is_device_ptr(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
     cudaGetLastError();
@@ -174,7 +166,7 @@ static int do_encode(lg_matrix* h, const uint64_t* preenc_u) {
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(h->owner, preenc_u, m.rows * m.k, &dev, &to_free));
-  int s = encode_rows(c, dev, m.rows, m.log_k, m.rho_inv, m.u);
+  int s = encode_rows(c, dev, m.rows, m.log_k, m.rho_inv, m.u, m.u + m.rows * m.k);
   if (to_free) {
     cudaStreamSynchronize(c->stream);
     cudaFree(to_free);

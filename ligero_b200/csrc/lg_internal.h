@@ -88,7 +88,16 @@ struct Matrix {
 
 // ---- kernel launchers (all stream-ordered on ctx->stream) -------------------------------------------
 // Reed-Solomon row encoding: msg (R x k, Montgomery, row-major, device) -> planes (a2+a3)
-int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* u_planes);
+// plane0 (nullable) receives a copy of the message; cosets receives the rho_inv-1 planes s = 1..rho_inv-1
+int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets);
+// protocol.cu
+int expand_fr(Ctx* ctx, const uint8_t seed[32], size_t count, Fr* out_dev);
+int col_reduce(Ctx* ctx, int mode, const Fr* W, const Fr* X, const Fr* Y, const Fr* Z, size_t rows, size_t k, Fr* out,
+               size_t out_stride, size_t out_offset);
+int spmv_right_block(Ctx* ctx, const uint32_t* col_ptr, const uint32_t* row_idx, const uint32_t* val_id, const Fr* consts,
+                     const Fr* r, size_t mk, Fr* out);
+struct Matrix;
+int gather_open(Ctx* ctx, const Matrix& m, const uint64_t* idx_dev, size_t t, Fr* cols_dev, uint8_t* sib_dev, uint8_t* auth_dev);
 // batched inverse NTT of `rows` rows of length 2^log_k, natural order in and out, includes 1/k
 int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k);
 // column hashing (a4+a5): leaves[j] = BLAKE2s(u64le(R) || canonical LE bytes of column j)

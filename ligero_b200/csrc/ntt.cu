@@ -146,7 +146,7 @@ struct LocalArgs {
   int q;                // log2 k
   int l;                // local stages = min(q, LOG_E)
   int rho;              // cosets (MODE 0)
-  int copy_plane0;      // MODE 0: also store the input to plane 0 (only when `in` is the message)
+  Fr* plane0;           // MODE 0: if non-null, also store the input here (only when `in` is the message)
   const Fr* w_fwd;      // order-2^l tables (compact: every local stage indexes a dense 2^(l-1)-entry array)
   const Fr* w_inv;
   const Fr* scale;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
     if (f < a.total) x = ld_fr(a.in + f);
     nz |= fr_or(x);
     sts_fr(Alo, Ahi, i, x);
-    if (MODE == 0 && a.copy_plane0 && f < a.total) st_fr(a.out + f, x);
+    if (MODE == 0 && a.plane0 && f < a.total) st_fr(a.plane0 + f, x);
   }
   const int any = __syncthreads_or(nz != 0);
   if (!any) {  // all-zero rows: codeword / coefficients are zero
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
     if (MODE == 0) {
       for (int s = 1; s < a.rho; s++)
         for (int i = threadIdx.x; i < E; i += NT)
-          if (f0 + i < a.total) st_fr(a.out + s * a.plane_stride + f0 + i, z);
+          if (f0 + i < a.total) st_fr(a.out + (s - 1) * a.plane_stride + f0 + i, z);
     } else {
       for (int i = threadIdx.x; i < E; i += NT)
         if (f0 + i < a.total) st_fr(a.out + f0 + i, z);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
       __syncthreads();
       s += r;
     }
-    Fr* dst = a.out + cs * a.plane_stride + f0;
+    Fr* dst = a.out + (cs - 1) * a.plane_stride + f0;
     for (int i = threadIdx.x; i < E; i += NT)
       if (f0 + i < a.total) st_fr(dst + i, lds_fr(Blo, Bhi, i));
     __syncthreads();
@@ -366,7 +366,7 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
   return launch_local_v<kMaxR, kMinB, MODE>(ctx, a);
 }
 
-int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* u) {
+int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets) {
   if (rows == 0) return OK;
   if ((rows << log_k) >= ((size_t)1 << 42)) return set_error(ctx, ERR_INVALID, "matrix too large");
   const NttTables* t;
@@ -376,7 +376,7 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
   if (l != q) LG_TRY(get_tables(ctx, l, 1, &tl));
   const size_t total = rows << q;
   LocalArgs a{};
-  a.out = u;
+  a.out = cosets;
   a.total = total;
   a.plane_stride = total;
   a.q = q;
@@ -393,22 +393,22 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
     bool first = true;
     for (int top = q; top > l;) {
       const int r = pass_radix(top - l), s = top - r;
-      LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, first ? u : nullptr, rows, q, s, t->w_inv));
+      LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, first ? plane0 : nullptr, rows, q, s, t->w_inv));
       src = (const Fr*)tmp;
       first = false;
       top = s;
     }
     a.in = (const Fr*)tmp;
-    a.copy_plane0 = 0;
+    a.plane0 = nullptr;
     phase_mark(ctx, PH_NTT_STRIDED_INV);
   } else {
     a.in = msg;
-    a.copy_plane0 = 1;
+    a.plane0 = plane0;
   }
   LG_TRY(launch_local<0>(ctx, a));
   phase_mark(ctx, PH_NTT_LOCAL);
   if (q > l && rho_inv > 1) {
-    Fr* p = u + total;
+    Fr* p = cosets;
     for (int s = l; s < q;) {
       const int r = pass_radix(q - s);
       LG_TRY(launch_global_pass_r<false>(ctx, r, p, p, nullptr, rows * (size_t)(rho_inv - 1), q, s, t->w_fwd));
