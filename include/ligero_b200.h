@@ -81,6 +81,18 @@ int lg_matrix_dims(const lg_matrix* m, size_t* rows, size_t* k, size_t* n);
 /* encode only (a2+a3), result left on the device; lg_matrix_hash then does a4-a6 on it */
 int lg_encode(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out);
 int lg_matrix_hash(lg_matrix* m, uint8_t root_out[32]);
+/* a handle over a CALLER-OWNED device buffer of rho_inv*rows*k Fr in the plane layout
+ * plane[s][i][c] = U[i][rho_inv*c + s] (multi-GPU: the row shard that is encoded into, and the column
+ * shard that arrives over NVLink); lg_matrix_free leaves the buffer alone */
+int lg_matrix_wrap(lg_ctx* ctx, uint64_t* u_dev, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out);
+/* a2+a3 into an existing handle (stream-ordered, returns without synchronising) */
+int lg_matrix_encode(lg_matrix* m, const uint64_t* preenc_u);
+
+/* device addresses of the resident arrays (stream-ordered interop with the caller's own kernels /
+ * collectives): U in the plane layout, n*32 leaf bytes, (n-1)*32 node bytes (node 0 = root) */
+void* lg_matrix_u_dev(const lg_matrix* m);
+void* lg_matrix_leaves_dev(const lg_matrix* m);
+void* lg_matrix_nodes_dev(const lg_matrix* m);
 
 /* read-backs (parity tests, debugging): U rows in the reference's logical column order */
 int lg_matrix_read_rows(const lg_matrix* m, size_t row0, size_t nrows, uint64_t* out /* Fr[nrows*n] */);

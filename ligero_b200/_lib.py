@@ -38,6 +38,11 @@ SIGNATURES = {
     "lg_matrix_dims": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
     "lg_encode": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p)]),
     "lg_matrix_hash": (c_int, [c_void_p, c_void_p]),
+    "lg_matrix_wrap": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p)]),
+    "lg_matrix_encode": (c_int, [c_void_p, c_void_p]),
+    "lg_matrix_u_dev": (c_void_p, [c_void_p]),
+    "lg_matrix_leaves_dev": (c_void_p, [c_void_p]),
+    "lg_matrix_nodes_dev": (c_void_p, [c_void_p]),
     "lg_matrix_read_rows": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p]),
     "lg_matrix_read_leaves": (c_int, [c_void_p, c_void_p]),
     "lg_matrix_read_nodes": (c_int, [c_void_p, c_void_p]),

@@ -121,6 +121,14 @@ class Context:
         check(self.lib.lg_encode(self.handle, _ptr(preenc_u), rows, k, rho_inv, byref(h)), self.handle, "lg_encode")
         return CommittedMatrix(self, h, None)
 
+    def wrap(self, u_dev, rows: int, k: int, rho_inv: int = 8) -> "CommittedMatrix":
+        """lg_matrix_wrap: handle over a caller-owned device buffer (torch tensor) in the plane layout."""
+        h = c_void_p()
+        check(self.lib.lg_matrix_wrap(self.handle, _ptr(u_dev), rows, k, rho_inv, byref(h)), self.handle, "lg_matrix_wrap")
+        cm = CommittedMatrix(self, h, None)
+        cm._keepalive = u_dev
+        return cm
+
     def intt(self, evals, rows: int, size: int, out=None):
         if out is None:
             out = np.empty((rows * size, 4), dtype=np.uint64)
@@ -211,6 +219,13 @@ class CommittedMatrix:
         check(self.ctx.lib.lg_recommit(self.handle, _ptr(preenc_u), _ptr(root)), self.ctx.handle, "lg_recommit")
         self.root = bytes(root)
         return self.root
+
+    def encode(self, preenc_u):
+        check(self.ctx.lib.lg_matrix_encode(self.handle, _ptr(preenc_u)), self.ctx.handle, "lg_matrix_encode")
+
+    def hash_async(self):
+        """column hashing + tree, no synchronisation (root stays on the device)."""
+        check(self.ctx.lib.lg_matrix_hash(self.handle, None), self.ctx.handle, "lg_matrix_hash")
 
     def hash(self) -> bytes:
         root = np.zeros(32, dtype=np.uint8)

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) bench_imad_wide_kernel(uint64_t* io, int 
   io[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
 
-static int matrix_alloc(lg_ctx* ctx, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out) {
+static int matrix_alloc(lg_ctx* ctx, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out, void* external_u = nullptr) {
   Ctx* c = &ctx->c;
   if (!out) return set_error(c, ERR_INVALID, "null output handle");
   if (rows == 0) return set_error(c, ERR_INVALID, "rows must be > 0");
@@ -123,12 +123,18 @@ static int matrix_alloc(lg_ctx* ctx, size_t rows, size_t k, uint32_t rho_inv, lg
   m.rho_inv = (int)rho_inv;
   m.k = k;
   m.n = k * rho_inv;
-  cudaError_t e = cudaMalloc(&m.u, m.n * rows * sizeof(Fr));
+  cudaError_t e = cudaSuccess;
+  if (external_u) {
+    m.u = (Fr*)external_u;
+    m.owns_u = false;
+  } else {
+    e = cudaMalloc(&m.u, m.n * rows * sizeof(Fr));
+  }
   if (e == cudaSuccess) e = cudaMalloc(&m.leaves, m.n * 32);
   if (e == cudaSuccess) e = cudaMalloc(&m.nodes, m.n * 32);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    if (m.u) cudaFree(m.u);
+    if (m.u && m.owns_u) cudaFree(m.u);
     if (m.leaves) cudaFree(m.leaves);
     if (m.nodes) cudaFree(m.nodes);
     delete h;
@@ -296,6 +302,19 @@ int lg_encode(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint
   return OK;
 }
 
+int lg_matrix_wrap(lg_ctx* ctx, uint64_t* u_dev, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out) {
+  if (!ctx) return ERR_INVALID;
+  cudaSetDevice(ctx->c.device);
+  if (!u_dev || !is_device_ptr(u_dev)) return set_error(&ctx->c, ERR_INVALID, "lg_matrix_wrap needs a device buffer");
+  return matrix_alloc(ctx, rows, k, rho_inv, out, u_dev);
+}
+
+int lg_matrix_encode(lg_matrix* m, const uint64_t* preenc_u) {
+  if (!m) return ERR_INVALID;
+  cudaSetDevice(m->m.ctx->device);
+  return do_encode(m, preenc_u);
+}
+
 int lg_matrix_hash(lg_matrix* m, uint8_t root_out[32]) {
   if (!m) return ERR_INVALID;
   cudaSetDevice(m->m.ctx->device);
@@ -341,6 +360,10 @@ int lg_matrix_dims(const lg_matrix* m, size_t* rows, size_t* k, size_t* n) {
   if (n) *n = m->m.n;
   return OK;
 }
+
+void* lg_matrix_u_dev(const lg_matrix* m) { return m ? (void*)m->m.u : nullptr; }
+void* lg_matrix_leaves_dev(const lg_matrix* m) { return m ? (void*)m->m.leaves : nullptr; }
+void* lg_matrix_nodes_dev(const lg_matrix* m) { return m ? (void*)m->m.nodes : nullptr; }
 
 int lg_matrix_read_rows(const lg_matrix* h, size_t row0, size_t nrows, uint64_t* out) {
   if (!h || !out) return ERR_INVALID;

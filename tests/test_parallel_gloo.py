@@ -1,0 +1,99 @@
+"""world_size-2 (and 4) gloo tests of the multi-GPU host logic on CPU: row partition, pack -> exchange ->
+unpack index math, subtree roots and the top of the tree.  The per-shard arithmetic that the GPUs do is
+stood in for by the oracle here (this is a test of the plumbing, which is shared with the NCCL path)."""
+import os
+import random
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ligero_b200 import fr_to_limbs, limbs_to_fr
+from ligero_b200 import parallel as par
+from oracle import ligero_oracle as O
+
+P = O.P
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, m, k, rho, seed, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rnd = random.Random(seed)
+        msg = [[rnd.randrange(P) for _ in range(k)] for _ in range(4 * m)]      # same matrix on every rank
+        dk, dn = O.Domain(k), O.Domain(rho * k)
+        ids = par.local_row_ids(m, world, rank)
+        # stand-in for the GPU encode of the local rows, in the plane layout [rho][rows_g][k]
+        u_local = [dn.fft(dk.ifft(msg[i])) for i in ids]
+        planes = np.zeros((rho, max(len(ids), 1), k, 4), dtype=np.uint64)
+        for li, row in enumerate(u_local):
+            limbs = fr_to_limbs(row).reshape(k, rho, 4)         # row[rho*c + s] -> [c][s]
+            planes[:, li] = limbs.transpose(1, 0, 2)
+        u_rows = torch.from_numpy(planes.view(np.int64))
+        kg = k // world
+        send = par.pack_for_exchange(u_rows[:, : len(ids)], rho, len(ids), k, world)
+        recv = [torch.empty((rho, 4 * (b - a), kg, 4), dtype=torch.int64) for a, b in par.block_slices(m, world)]
+        par.exchange(send, recv)
+        u_cols = torch.empty((rho, 4 * m, kg, 4), dtype=torch.int64)
+        par.unpack_after_exchange(recv, u_cols, m, world, rho, kg)
+        cols = u_cols.numpy().view(np.uint64)                    # [rho][4m][kg][4]
+        # column shard -> leaves of the contiguous range [rank*n/G, (rank+1)*n/G)
+        leaves = []
+        for c in range(kg):
+            for s in range(rho):
+                col = limbs_to_fr(cols[s, :, c])
+                leaves.append(O.column_hash(col))
+        sub = O.MerkleTree(leaves).root()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, sub)
+        root = par.combine_subtree_roots(gathered)
+        # ground truth: the unsharded oracle
+        u = [dn.fft(dk.ifft(r)) for r in msg]
+        want = O.MerkleTree([O.column_hash([u[i][j] for i in range(4 * m)]) for j in range(rho * k)]).root()
+        q.put((rank, root == want))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,m,k,rho", [(2, 3, 8, 8), (2, 2, 4, 4), (4, 5, 16, 8)])
+def test_sharded_commit_plumbing_matches_unsharded_root(world, m, k, rho):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, m, k, rho, 11, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in results), results
+
+
+def test_partition_covers_every_row_once():
+    for m in (1, 2, 5, 86, 4097):
+        for world in (1, 2, 4, 8):
+            ids = sorted(i for r in range(world) for i in par.local_row_ids(m, world, r))
+            assert ids == list(range(4 * m))
+            sizes = [b - a for a, b in par.block_slices(m, world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_top_of_tree():
+    import hashlib
+    roots = [bytes([i]) * 32 for i in range(4)]
+    l0 = hashlib.sha256(roots[0] + roots[1]).digest()
+    l1 = hashlib.sha256(roots[2] + roots[3]).digest()
+    assert par.combine_subtree_roots(roots) == hashlib.sha256(l0 + l1).digest()
+    assert par.combine_subtree_roots(roots[:1]) == roots[0]
