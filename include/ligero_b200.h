@@ -88,6 +88,25 @@ int lg_matrix_wrap(lg_ctx* ctx, uint64_t* u_dev, size_t rows, size_t k, uint32_t
 /* a2+a3 into an existing handle (stream-ordered, returns without synchronising) */
 int lg_matrix_encode(lg_matrix* m, const uint64_t* preenc_u);
 
+/* ---- multi-GPU: one process per GPU, rows sharded for encoding, column ranges for hashing ------ */
+/* an un-encoded handle of the given shape (U allocated with cudaMalloc so that it can be exported) */
+int lg_matrix_create(lg_ctx* ctx, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out);
+/* CUDA IPC: export the U buffer of a handle / map a peer's exported buffer into this process
+ * (peer access over NVLink is enabled lazily by the driver) */
+int lg_ipc_export(const lg_matrix* m, uint8_t handle_out[64]);
+int lg_ipc_open(lg_ctx* ctx, const uint8_t handle[64], void** ptr_out);
+int lg_ipc_close(lg_ctx* ctx, void* ptr);
+/* Encode this rank's rows and scatter every finished codeword element -- from inside the last NTT pass,
+ * over peer memory -- into the column shard of the rank that owns its message index:
+ *   msg_local : Fr[4*m_g*k], the rows {b*m + i0 + i : b < 4, i < m_g} of the 4m x k matrix, [X_g;Y_g;Z_g;W_g]
+ *   shard_u   : world device pointers; shard_u[h] = U buffer of rank h's column shard, a plane-layout
+ *               matrix of 4m rows x (k/world) columns (this rank's own plus lg_ipc_open'ed peers)
+ *   cosets_scratch : device Fr[(rho_inv-1)*4*m_g*k], needed when k > 1024 (may be NULL otherwise)
+ * Stream-ordered; the caller synchronises all ranks (e.g. an NCCL all-reduce on the context stream)
+ * before hashing the shards. */
+int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t k, uint32_t rho_inv, void* const* shard_u,
+                      int world, size_t m, size_t i0, uint64_t* cosets_scratch);
+
 /* device addresses of the resident arrays (stream-ordered interop with the caller's own kernels /
  * collectives): U in the plane layout, n*32 leaf bytes, (n-1)*32 node bytes (node 0 = root) */
 void* lg_matrix_u_dev(const lg_matrix* m);

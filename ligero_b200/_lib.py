@@ -40,6 +40,12 @@ SIGNATURES = {
     "lg_matrix_hash": (c_int, [c_void_p, c_void_p]),
     "lg_matrix_wrap": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p)]),
     "lg_matrix_encode": (c_int, [c_void_p, c_void_p]),
+    "lg_matrix_create": (c_int, [c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p)]),
+    "lg_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "lg_ipc_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
+    "lg_ipc_close": (c_int, [c_void_p, c_void_p]),
+    "lg_encode_sharded": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p), c_int, c_size_t,
+                                  c_size_t, c_void_p]),
     "lg_matrix_u_dev": (c_void_p, [c_void_p]),
     "lg_matrix_leaves_dev": (c_void_p, [c_void_p]),
     "lg_matrix_nodes_dev": (c_void_p, [c_void_p]),

@@ -361,6 +361,78 @@ int lg_matrix_dims(const lg_matrix* m, size_t* rows, size_t* k, size_t* n) {
   return OK;
 }
 
+int lg_matrix_create(lg_ctx* ctx, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out) {
+  if (!ctx) return ERR_INVALID;
+  cudaSetDevice(ctx->c.device);
+  return matrix_alloc(ctx, rows, k, rho_inv, out);
+}
+
+int lg_ipc_export(const lg_matrix* m, uint8_t handle_out[64]) {
+  if (!m || !handle_out) return ERR_INVALID;
+  Ctx* c = m->m.ctx;
+  cudaSetDevice(c->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  LG_CUDA(c, cudaIpcGetMemHandle(&h, m->m.u));
+  memcpy(handle_out, &h, 64);
+  return OK;
+}
+
+int lg_ipc_open(lg_ctx* ctx, const uint8_t handle[64], void** ptr_out) {
+  if (!ctx || !handle || !ptr_out) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  LG_CUDA(c, cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return OK;
+}
+
+int lg_ipc_close(lg_ctx* ctx, void* ptr) {
+  if (!ctx) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  LG_CUDA(c, cudaIpcCloseMemHandle(ptr));
+  return OK;
+}
+
+int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t k, uint32_t rho_inv, void* const* shard_u,
+                      int world, size_t m, size_t i0, uint64_t* cosets_scratch) {
+  if (!ctx || !shard_u) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (world < 1 || world > kMaxRanks || (world & (world - 1))) return set_error(c, ERR_INVALID, "world must be a power of two <= 8");
+  if (k < 2 || (k & (k - 1)) || k % world) return set_error(c, ERR_INVALID, "k must be a power of two divisible by world");
+  if (i0 + m_g > m) return set_error(c, ERR_INVALID, "row slice out of range");
+  if (m_g == 0) return OK;
+  if (!msg_local) return set_error(c, ERR_INVALID, "null input matrix");
+  int log_k = 0, log_w = 0;
+  while (((size_t)1 << log_k) < k) log_k++;
+  while ((1 << log_w) < world) log_w++;
+  if (log_k > 10 && !cosets_scratch) return set_error(c, ERR_INVALID, "rows longer than 1024 need the local coset scratch buffer");
+  OutMap map{};
+  for (int g = 0; g < world; g++) {
+    if (!shard_u[g]) return set_error(c, ERR_INVALID, "null shard pointer");
+    map.base[g] = (Fr*)shard_u[g];
+  }
+  map.log_kg = log_k - log_w;
+  map.m = (uint32_t)m;
+  map.m_g = (uint32_t)m_g;
+  map.i0 = (uint32_t)i0;
+  map.rows_total = 4ull * m;
+  const size_t rows = 4 * m_g;
+  const Fr* dev;
+  void* to_free;
+  LG_TRY(stage_input(ctx, msg_local, rows * k, &dev, &to_free));
+  int s = encode_rows(c, dev, rows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map);
+  if (to_free) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(to_free);
+  }
+  return s;
+}
+
 void* lg_matrix_u_dev(const lg_matrix* m) { return m ? (void*)m->m.u : nullptr; }
 void* lg_matrix_leaves_dev(const lg_matrix* m) { return m ? (void*)m->m.leaves : nullptr; }
 void* lg_matrix_nodes_dev(const lg_matrix* m) { return m ? (void*)m->m.nodes : nullptr; }

@@ -86,10 +86,36 @@ struct Matrix {
   bool owns_u = true;
 };
 
+// ---- where a codeword element goes -------------------------------------------------------------------
+// Single GPU: the local plane layout.  Multi GPU: the encode kernels store every finished element
+// straight into the column shard of the rank that owns its message index c (peer memory over NVLink,
+// mapped with CUDA IPC), at its GLOBAL row position -- the all-to-all is fused into the last NTT pass.
+//   element (plane s, local row i, column c)  ->  base[c >> log_kg] + ((s*rows_total + grow(i)) << log_kg) + (c mod kg)
+//   grow(i) = (i / m_g) * m + i0 + i % m_g     (local rows are [X_g; Y_g; Z_g; W_g], m_g rows per block)
+constexpr int kMaxRanks = 8;
+struct OutMap {
+  Fr* base[kMaxRanks];
+  int log_kg;
+  uint32_t m, m_g, i0;
+  unsigned long long rows_total;
+};
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint32_t outmap_row(const OutMap& o, uint32_t i_local) {
+  const uint32_t b = i_local / o.m_g;
+  return b * o.m + o.i0 + (i_local - b * o.m_g);
+}
+__device__ __forceinline__ Fr* outmap_ptr(const OutMap& o, uint32_t s, uint32_t grow, uint32_t c) {
+  return o.base[c >> o.log_kg] + ((((unsigned long long)s * o.rows_total + grow) << o.log_kg) + (c & ((1u << o.log_kg) - 1u)));
+}
+#endif
+
 // ---- kernel launchers (all stream-ordered on ctx->stream) -------------------------------------------
 // Reed-Solomon row encoding: msg (R x k, Montgomery, row-major, device) -> planes (a2+a3)
 // plane0 (nullable) receives a copy of the message; cosets receives the rho_inv-1 planes s = 1..rho_inv-1
-int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets);
+// map (nullable): final destination of every element (multi-GPU); `cosets` is then only the local
+// intermediate of rows longer than one CTA tile and plane0 is ignored
+int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets,
+                const OutMap* map = nullptr);
 // protocol.cu
 int expand_fr(Ctx* ctx, const uint8_t seed[32], size_t count, Fr* out_dev);
 int col_reduce(Ctx* ctx, int mode, const Fr* W, const Fr* X, const Fr* Y, const Fr* Z, size_t rows, size_t k, Fr* out,

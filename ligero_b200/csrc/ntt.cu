@@ -151,7 +151,16 @@ struct LocalArgs {
   const Fr* w_inv;
   const Fr* scale;
   Fr kinv;              // MODE 1: 1/k
+  int mapped;           // MODE 0: 1 = finished elements (and the plane-0 copy) go through `map`
+  int copy0;            // MODE 0, mapped: also store the input as plane 0
+  OutMap map;
 };
+
+// mapped store of element `f` (flat index into the local rows x k array) of coset plane s
+__device__ __forceinline__ void st_mapped(const LocalArgs& a, uint32_t s, unsigned long long f, const Fr& x) {
+  const uint32_t row = (uint32_t)(f >> a.q), col = (uint32_t)f & ((1u << a.q) - 1u);
+  st_fr(outmap_ptr(a.map, s, outmap_row(a.map, row), col), x);
+}
 
 // MODE 0: encode (iNTT tail + all cosets).  MODE 1: iNTT tail only, scaled, natural-order output.
 template <int LOG_E, int MAXR, int MINB, int MODE>
@@ -170,7 +179,13 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
     if (f < a.total) x = ld_fr(a.in + f);
     nz |= fr_or(x);
     sts_fr(Alo, Ahi, i, x);
-    if (MODE == 0 && a.plane0 && f < a.total) st_fr(a.plane0 + f, x);
+    if (MODE == 0 && f < a.total) {
+      if (a.mapped) {
+        if (a.copy0) st_mapped(a, 0, f, x);
+      } else if (a.plane0) {
+        st_fr(a.plane0 + f, x);
+      }
+    }
   }
   const int any = __syncthreads_or(nz != 0);
   if (!any) {  // all-zero rows: codeword / coefficients are zero
@@ -178,7 +193,10 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
     if (MODE == 0) {
       for (int s = 1; s < a.rho; s++)
         for (int i = threadIdx.x; i < E; i += NT)
-          if (f0 + i < a.total) st_fr(a.out + (s - 1) * a.plane_stride + f0 + i, z);
+          if (f0 + i < a.total) {
+            if (a.mapped) st_mapped(a, s, f0 + i, z);
+            else st_fr(a.out + (s - 1) * a.plane_stride + f0 + i, z);
+          }
     } else {
       for (int i = threadIdx.x; i < E; i += NT)
         if (f0 + i < a.total) st_fr(a.out + f0 + i, z);
@@ -218,7 +236,10 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
     }
     Fr* dst = a.out + (cs - 1) * a.plane_stride + f0;
     for (int i = threadIdx.x; i < E; i += NT)
-      if (f0 + i < a.total) st_fr(dst + i, lds_fr(Blo, Bhi, i));
+      if (f0 + i < a.total) {
+        if (a.mapped) st_mapped(a, cs, f0 + i, lds_fr(Blo, Bhi, i));
+        else st_fr(dst + i, lds_fr(Blo, Bhi, i));
+      }
     __syncthreads();
   }
 }
@@ -247,6 +268,39 @@ __global__ void __launch_bounds__(256) ntt_global_pass_kernel(const Fr* in, Fr* 
   if (nz != 0) butterflies<R, DIF>(x, t_lo, s, q, W);
 #pragma unroll
   for (int e = 0; e < (1 << R); e++) st_fr(out + off + (base | ((uint32_t)e << s)), x[e]);
+}
+
+// the same pass with mapped stores (multi-GPU): COPY0 -> the loaded input is plane 0 of row blockIdx.x and
+// the transformed values go to the local `out`; otherwise `in` holds rows_per_plane rows per coset plane
+// (plane 1 first) and the transformed values are final and go through the map
+template <int R, bool DIF, bool COPY0>
+__global__ void __launch_bounds__(256) ntt_global_pass_mapped_kernel(const Fr* in, Fr* out, int q, int s,
+                                                                     const Fr* __restrict__ W, const OutMap map,
+                                                                     uint32_t rows_per_plane) {
+  const uint32_t g = blockIdx.y * blockDim.x + threadIdx.x;
+  if (g >= (1u << (q - R))) return;
+  const size_t off = (size_t)blockIdx.x << q;
+  const uint32_t t_lo = g & ((1u << s) - 1u), t_hi = g >> s;
+  const uint32_t base = (t_hi << (s + R)) | t_lo;
+  const uint32_t plane = COPY0 ? 0u : 1u + blockIdx.x / rows_per_plane;
+  const uint32_t grow = outmap_row(map, COPY0 ? blockIdx.x : blockIdx.x % rows_per_plane);
+  Fr x[1 << R];
+  uint32_t nz = 0;
+#pragma unroll
+  for (int e = 0; e < (1 << R); e++) {
+    x[e] = ld_fr(in + off + (base | ((uint32_t)e << s)));
+    nz |= fr_or(x[e]);
+  }
+  if (COPY0) {
+#pragma unroll
+    for (int e = 0; e < (1 << R); e++) st_fr(outmap_ptr(map, 0, grow, base | ((uint32_t)e << s)), x[e]);
+  }
+  if (nz != 0) butterflies<R, DIF>(x, t_lo, s, q, W);
+#pragma unroll
+  for (int e = 0; e < (1 << R); e++) {
+    if (COPY0) st_fr(out + off + (base | ((uint32_t)e << s)), x[e]);
+    else st_fr(outmap_ptr(map, plane, grow, base | ((uint32_t)e << s)), x[e]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,9 +420,28 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
   return launch_local_v<kMaxR, kMinB, MODE>(ctx, a);
 }
 
-int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets) {
+template <int R, bool DIF, bool COPY0>
+static int launch_global_pass_mapped(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int q, int s, const Fr* W,
+                                     const OutMap& map, uint32_t rows_per_plane) {
+  const uint32_t groups = 1u << (q - R);
+  const uint32_t bs = groups < 256 ? groups : 256;
+  dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
+  ntt_global_pass_mapped_kernel<R, DIF, COPY0><<<grid, bs, 0, ctx->stream>>>(in, out, q, s, W, map, rows_per_plane);
+  ctx->launches++;
+  LG_CUDA(ctx, cudaGetLastError());
+  return OK;
+}
+template <bool DIF, bool COPY0>
+static int launch_global_pass_mapped_r(Ctx* ctx, int r, const Fr* in, Fr* out, size_t rows, int q, int s, const Fr* W,
+                                       const OutMap& map, uint32_t rows_per_plane) {
+  if (r == 3) return launch_global_pass_mapped<3, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
+  if (r == 2) return launch_global_pass_mapped<2, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
+  return launch_global_pass_mapped<1, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
+}
+
+int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets, const OutMap* map) {
   if (rows == 0) return OK;
-  if ((rows << log_k) >= ((size_t)1 << 42)) return set_error(ctx, ERR_INVALID, "matrix too large");
+  if ((rows << log_k) >= ((size_t)1 << 42) || rows >= ((size_t)1 << 31)) return set_error(ctx, ERR_INVALID, "matrix too large");
   const NttTables* t;
   LG_TRY(get_tables(ctx, log_k, rho_inv, &t));
   const int q = log_k, l = q < kLogE ? q : kLogE;
@@ -385,6 +458,7 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
   a.w_fwd = tl->w_fwd;
   a.w_inv = tl->w_inv;
   a.scale = t->scale;
+  if (map) a.map = *map;
   phase_mark(ctx, PH_BEGIN);
   if (q > l) {
     void* tmp;
@@ -393,25 +467,35 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
     bool first = true;
     for (int top = q; top > l;) {
       const int r = pass_radix(top - l), s = top - r;
-      LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, first ? plane0 : nullptr, rows, q, s, t->w_inv));
+      if (first && map)
+        LG_TRY((launch_global_pass_mapped_r<true, true>(ctx, r, src, (Fr*)tmp, rows, q, s, t->w_inv, *map, (uint32_t)rows)));
+      else
+        LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, first ? plane0 : nullptr, rows, q, s, t->w_inv));
       src = (const Fr*)tmp;
       first = false;
       top = s;
     }
     a.in = (const Fr*)tmp;
     a.plane0 = nullptr;
+    a.mapped = 0;  // the local kernel writes the intermediate; the last strided pass does the mapped stores
     phase_mark(ctx, PH_NTT_STRIDED_INV);
   } else {
     a.in = msg;
     a.plane0 = plane0;
+    a.mapped = map ? 1 : 0;
+    a.copy0 = map ? 1 : 0;
   }
   LG_TRY(launch_local<0>(ctx, a));
   phase_mark(ctx, PH_NTT_LOCAL);
   if (q > l && rho_inv > 1) {
     Fr* p = cosets;
+    const size_t prow = rows * (size_t)(rho_inv - 1);
     for (int s = l; s < q;) {
       const int r = pass_radix(q - s);
-      LG_TRY(launch_global_pass_r<false>(ctx, r, p, p, nullptr, rows * (size_t)(rho_inv - 1), q, s, t->w_fwd));
+      if (map && s + r == q)
+        LG_TRY((launch_global_pass_mapped_r<false, false>(ctx, r, p, nullptr, prow, q, s, t->w_fwd, *map, (uint32_t)rows)));
+      else
+        LG_TRY(launch_global_pass_r<false>(ctx, r, p, p, nullptr, prow, q, s, t->w_fwd));
       s += r;
     }
     phase_mark(ctx, PH_NTT_STRIDED_FWD);

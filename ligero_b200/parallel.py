@@ -96,29 +96,81 @@ def exchange(send: List[torch.Tensor], recv: List[torch.Tensor]) -> None:
 # device path
 # --------------------------------------------------------------------------------------------
 class ShardedCommitter:
-    """Row-sharded encode -> NVLink exchange -> column-sharded hash + subtree -> root all-gather."""
+    """Row-sharded encode -> exchange -> column-sharded hash + subtree -> root all-gather.
 
-    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int):
+    mode "fused" (default): the exchange is fused into the encode kernels -- the last NTT pass stores each
+        finished element directly into the owning rank's column shard over NVLink peer memory (CUDA IPC
+        mappings exchanged once at construction), so the transfer overlaps the butterflies and there is no
+        pack / all-to-all / unpack; one tiny NCCL all-reduce orders the ranks before hashing.
+    mode "nccl": encode locally, then pack -> NCCL all_to_all -> unpack (the plain-library baseline, and the
+        plumbing the gloo tests cover).
+    """
+
+    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int, mode: str = "fused"):
         assert world & (world - 1) == 0 and k % world == 0 and (rho * k // world) >= 2
-        self.ctx, self.m, self.k, self.rho, self.rank, self.world = ctx, m, k, rho, rank, world
+        assert mode in ("fused", "nccl")
+        self.ctx, self.m, self.k, self.rho, self.rank, self.world, self.mode = ctx, m, k, rho, rank, world, mode
         self.slices = block_slices(m, world)
         i0, i1 = self.slices[rank]
-        self.m_g = i1 - i0
+        self.i0, self.m_g = i0, i1 - i0
         self.rows_g = 4 * self.m_g
         self.kg = k // world
         dev = torch.device("cuda", ctx.device)
+        self.dev = dev
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-        self.u_rows = torch.empty((rho, max(self.rows_g, 1), k, 4), dtype=torch.int64, device=dev)
-        self.u_cols = torch.empty((rho, 4 * m, self.kg, 4), dtype=torch.int64, device=dev)
-        self.recv = [torch.empty((rho, 4 * (b - a), self.kg, 4), dtype=torch.int64, device=dev) for a, b in self.slices]
-        self.mat_rows = ctx.wrap(self.u_rows, max(self.rows_g, 1), k, rho) if self.rows_g else None
-        self.mat_cols = ctx.wrap(self.u_cols, 4 * m, self.kg, rho)
         self.roots = torch.empty((world, 32), dtype=torch.uint8, device=dev)
         self.my_root = torch.empty(32, dtype=torch.uint8, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._peer_ptrs = []
+        if mode == "nccl":
+            self.u_rows = torch.empty((rho, max(self.rows_g, 1), k, 4), dtype=torch.int64, device=dev)
+            self.u_cols = torch.empty((rho, 4 * m, self.kg, 4), dtype=torch.int64, device=dev)
+            self.recv = [torch.empty((rho, 4 * (b - a), self.kg, 4), dtype=torch.int64, device=dev) for a, b in self.slices]
+            self.mat_rows = ctx.wrap(self.u_rows, max(self.rows_g, 1), k, rho) if self.rows_g else None
+            self.mat_cols = ctx.wrap(self.u_cols, 4 * m, self.kg, rho)
+        else:
+            from ctypes import byref, c_void_p
+            import numpy as np
+            from .backend import CommittedMatrix, check
+            h = c_void_p()
+            check(ctx.lib.lg_matrix_create(ctx.handle, 4 * m, self.kg, rho, byref(h)), ctx.handle, "lg_matrix_create")
+            self.mat_cols = CommittedMatrix(ctx, h, None)
+            handle = np.zeros(64, dtype=np.uint8)
+            check(ctx.lib.lg_ipc_export(self.mat_cols.handle, handle.ctypes.data), ctx.handle, "lg_ipc_export")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle))
+            ptrs = []
+            for g in range(world):
+                if g == rank:
+                    ptrs.append(int(ctx.lib.lg_matrix_u_dev(self.mat_cols.handle)))
+                else:
+                    p = c_void_p()
+                    hb = np.frombuffer(handles[g], dtype=np.uint8).copy()
+                    check(ctx.lib.lg_ipc_open(ctx.handle, hb.ctypes.data, byref(p)), ctx.handle, "lg_ipc_open")
+                    ptrs.append(int(p.value))
+                    self._peer_ptrs.append(int(p.value))
+            self.shard_ptrs = (c_void_p * world)(*ptrs)
+            # local intermediate of the coset planes, only for rows longer than one CTA tile (k > 1024)
+            self.scratch = (torch.empty(((rho - 1) * max(self.rows_g, 1) * k, 4), dtype=torch.int64, device=dev)
+                            if k > 1024 else None)
+            dist.barrier()
+
+    def close(self):
+        if self._peer_ptrs:
+            self.ctx.sync()
+            dist.barrier()
+            for p in self._peer_ptrs:
+                self.ctx.lib.lg_ipc_close(self.ctx.handle, p)
+            self._peer_ptrs = []
+            dist.barrier()
+        if getattr(self, "mat_cols", None) is not None:
+            self.mat_cols.free()
 
     def commit_async(self, msg_local, marks=None) -> None:
         """Enqueue everything on the context stream; the root lands in self.roots (device).
         `marks`: optional list that receives (label, torch.cuda.Event) pairs for per-phase timing."""
+        from .backend import _ptr, check
+
         def mark(label):
             if marks is not None:
                 e = torch.cuda.Event(enable_timing=True)
@@ -126,15 +178,24 @@ class ShardedCommitter:
                 marks.append((label, e))
         with torch.cuda.stream(self.stream):
             mark("start")
-            if self.mat_rows is not None:
-                self.mat_rows.encode(msg_local)
-            mark("encode")
-            send = pack_for_exchange(self.u_rows[:, : self.rows_g], self.rho, self.rows_g, self.k, self.world)
-            mark("pack")
-            exchange(send, self.recv)
-            mark("exchange")
-            unpack_after_exchange(self.recv, self.u_cols, self.m, self.world, self.rho, self.kg)
-            mark("unpack")
+            if self.mode == "nccl":
+                if self.mat_rows is not None:
+                    self.mat_rows.encode(msg_local)
+                mark("encode")
+                send = pack_for_exchange(self.u_rows[:, : self.rows_g], self.rho, self.rows_g, self.k, self.world)
+                mark("pack")
+                exchange(send, self.recv)
+                mark("exchange")
+                unpack_after_exchange(self.recv, self.u_cols, self.m, self.world, self.rho, self.kg)
+                mark("unpack")
+            else:
+                check(self.ctx.lib.lg_encode_sharded(self.ctx.handle, _ptr(msg_local), self.m_g, self.k, self.rho,
+                                                     self.shard_ptrs, self.world, self.m, self.i0,
+                                                     _ptr(self.scratch) if self.scratch is not None else None),
+                      self.ctx.handle, "lg_encode_sharded")
+                mark("encode+scatter over NVLink")
+                dist.all_reduce(self.flag)      # every rank's stores have landed before anyone hashes
+                mark("rank barrier")
             self.mat_cols.hash_async()
             mark("hash+subtree")
             # subtree root = node 0 of the local tree (device -> device, stays on the stream)
@@ -164,10 +225,9 @@ class ShardedCommitter:
     @staticmethod
     def bench(ctx, R: int, k: int, rho: int, args, rank: int, world: int) -> dict:
         """bench.py's N > 1 path: strong scaling of one R x k encode+commit over `world` GPUs."""
-        import numpy as np
-        from .backend import _ptr
+        mode = os.environ.get("LG_MGPU_MODE", "fused")
         m = R // 4
-        sc = ShardedCommitter(ctx, m, k, rho, rank, world)
+        sc = ShardedCommitter(ctx, m, k, rho, rank, world, mode)
         dev = torch.device("cuda", ctx.device)
         g = torch.Generator(device=dev)
         g.manual_seed(20240 + rank)
@@ -210,12 +270,15 @@ class ShardedCommitter:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         assert r == root0
         e2e_ms = float(dt.item()) * 1e3 / args.steps
+        sc.close()
+        par = (f"rows/{world} encode with the column exchange fused into the last NTT pass (NVLink peer stores) -> "
+               f"column-range/{world} hash + subtree -> NCCL root all-gather") if mode == "fused" else \
+              f"rows/{world} encode -> NCCL all-to-all -> column-range/{world} hash + subtree -> root all-gather"
         return {
             "metric": "fr_elems_per_s_encode_commit", "value": value, "unit": "Fr elems/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 Montgomery (BN254 Fr)", "data": "synthetic",
-            "config": {"rows": R, "k": k, "n": rho * k, "rho_inv": rho,
-                       "parallelism": f"rows/{world} encode -> NVLink all-to-all -> column-range/{world} hash + subtree -> root all-gather",
+            "config": {"rows": R, "k": k, "n": rho * k, "rho_inv": rho, "parallelism": par,
                        "l2_policy": "inputs larger than L2"},
             "e2e": {"value": R * k / (e2e_ms * 1e-3), "unit": "Fr elems/s", "h2d_bytes_per_step": int(msg.numel() * 8) * world,
                     "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_ms,
