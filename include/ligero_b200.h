@@ -160,6 +160,76 @@ int lg_quadratic_test(lg_matrix* m, const uint64_t* r_quad, uint64_t* coeffs_out
  * auth_out: t*(log2(n)-1)*32 bytes, per column the sibling digests from just below the root downwards */
 int lg_open(lg_matrix* m, const uint64_t* idx, size_t t, uint64_t* cols_out, uint8_t* sib_out, uint8_t* auth_out);
 
+/* =====================================================================================================
+ * Host driver: the reference's public API over the primitives above (capi_host.cu).  Same names,
+ * argument meaning and failure behaviour as NP-Eng/ligero; panics become LG_ERR_* + lg_last_error.
+ * ===================================================================================================== */
+
+/* ---- ArithmeticCircuit: src/arithmetic_circuit/mod.rs ------------------------------------------- */
+typedef struct lg_circuit lg_circuit;
+int lg_circuit_new(lg_circuit** out);                                                      /* new, 65-72 */
+int lg_circuit_free(lg_circuit* c);
+const char* lg_circuit_last_error(const lg_circuit* c);
+int lg_circuit_constant(lg_circuit* c, const uint64_t value[4], size_t* index_out);        /* constant, 76-84 */
+int lg_circuit_new_variable(lg_circuit* c, const char* label /* NULL -> "var_N" */, size_t* index_out); /* 92-109 */
+int lg_circuit_get_variable(const lg_circuit* c, const char* label, size_t* index_out);    /* 115-117 */
+int lg_circuit_add(lg_circuit* c, size_t left, size_t right, size_t* index_out);           /* add, 125-131 */
+int lg_circuit_mul(lg_circuit* c, size_t left, size_t right, size_t* index_out);           /* mul, 139-145 */
+int lg_circuit_counts(const lg_circuit* c, size_t* nodes, size_t* constants, size_t* variables, size_t* gates); /* 38-63 */
+/* node inspection: type 0 = Variable, 1 = Constant, 2 = Add, 3 = Mul */
+int lg_circuit_node(const lg_circuit* c, size_t index, int* type, size_t* left, size_t* right, uint64_t value[4]);
+/* evaluate_multioutput, 325-400: out_vals = Fr[n_outputs] values of the output nodes */
+int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
+                        size_t n_outputs, uint64_t* out_vals);
+/* from_constraint_system, 455-520.  A, B, C as ConstraintSystem::to_matrices yields them, in CSR form:
+ * row_ptr[i][n_constraints+1], col_idx[i][nnz], coeffs[i] = Fr[nnz]; column 0 is the constant one and
+ * n_cols = num_instance_variables + num_witness_variables.  outputs: size_t[n_constraints]. */
+int lg_circuit_from_r1cs(size_t n_constraints, size_t n_cols, const uint64_t* const row_ptr[3], const uint64_t* const col_idx[3],
+                         const uint64_t* const coeffs[3], lg_circuit** out, size_t* outputs);
+
+/* ---- Fiat-Shamir sponge (host): ark-crypto-primitives PoseidonSponge ------------------------------ */
+typedef struct lg_sponge lg_sponge;
+/* PoseidonConfig::new(full, partial, alpha, mds, ark, rate, capacity); mds: Fr[(rate+cap)^2] row-major,
+ * ark: Fr[(full+partial)*(rate+cap)] */
+int lg_sponge_new(int full_rounds, int partial_rounds, uint64_t alpha, const uint64_t* mds, const uint64_t* ark, int rate, int capacity,
+                  lg_sponge** out);
+/* ark_poly_commit::test_sponge() with the deterministic ark_std::test_rng() (src/ligero/tests.rs:151,399) */
+int lg_sponge_test(lg_sponge** out);
+int lg_sponge_clone(const lg_sponge* s, lg_sponge** out);
+int lg_sponge_free(lg_sponge* s);
+int lg_sponge_absorb_bytes(lg_sponge* s, const uint8_t* data, size_t len); /* absorb(&Vec<u8>) */
+int lg_sponge_absorb_fr(lg_sponge* s, const uint64_t* elems, size_t count); /* absorb(&Vec<F>) */
+int lg_sponge_squeeze_bytes(lg_sponge* s, uint8_t* out, size_t len);
+
+/* ---- LigeroCircuit: src/ligero/mod.rs ---------------------------------------------------------------- */
+typedef struct lg_ligero lg_ligero;
+typedef struct lg_proof lg_proof;
+/* LigeroCircuit::new(circuit, outputs, lambda), 147-228 (the circuit is copied; constraint matrix A is
+ * built and uploaded once).  LG_ERR_UNSUPPORTED for gates with two constant operands (the reference panics). */
+int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_ligero** out);
+int lg_ligero_free(lg_ligero* l);
+int lg_ligero_params(const lg_ligero* l, size_t* m, size_t* k, size_t* n, size_t* t, size_t* sol_len);
+/* witness layout of prove_inner, 476-516: out = Fr[4*m*k] (host) = [X;Y;Z;W].  bump != 0: indices refer to
+ * the caller's circuit (as in `prove`), 0: to the formatted circuit (as in `prove_inner`). */
+int lg_ligero_witness_matrix(lg_ligero* l, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, uint64_t* out);
+/* prove, 435-455 (bump != 0) / prove_inner, 457-578 (bump == 0); the sponge is advanced in place */
+int lg_prove(lg_ligero* l, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out);
+/* prove_with_labels, 580-611 */
+int lg_prove_with_labels(lg_ligero* l, const char* const* labels, const uint64_t* var_vals, size_t n_vars, lg_sponge* sponge,
+                         lg_proof** out);
+/* the commit-and-test transcript on a ready pre-encoding matrix (Fr[4*m*k], host or device) */
+int lg_prove_matrix(lg_ligero* l, const uint64_t* preenc_u, lg_sponge* sponge, lg_proof** out);
+/* verify, 613-644: *accepted = 1 iff every check passes (0 otherwise; errors only for resource failures) */
+int lg_verify(lg_ligero* l, const lg_proof* proof, lg_sponge* sponge, int* accepted);
+int lg_proof_free(lg_proof* p);
+/* Proof wire format (the reference defines none: LigeroProof has no derives, mod.rs:96-144): the layout
+ * arkworks' CanonicalSerialize would give the same structs -- little endian, Vec<T> = u64 length + items,
+ * Fr = 32 canonical bytes, digests = Vec<u8>, Path = {leaf_sibling_hash, auth_path, leaf_index: u64}:
+ *   u_root | preenc_u_lc, columns, paths | linear poly coeffs, columns, paths | quadratic poly coeffs, columns, paths
+ * buf may be NULL to query the length. */
+int lg_proof_serialize(const lg_proof* p, uint8_t* buf, size_t cap, size_t* len_out);
+int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out);
+
 /* ---- measured integer roofline ----------------------------------------------------------------- */
 /* Runs dependent-chain microbenchmarks at full occupancy for ~`ms_target` milliseconds each and
  * reports sustained Montgomery multiplications/s and IMAD.WIDE.U32 (32x32+64) operations/s. */

@@ -6,3 +6,5 @@ without the built library or without a GPU raises LigeroB200Error.
 """
 from ._lib import LIB_PATH, LigeroB200Error  # noqa: F401
 from .backend import BN254_R, CommittedMatrix, Constraints, Context, fr_to_limbs, limbs_to_fr  # noqa: F401
+from .api import (ArithmeticCircuit, LigeroCircuit, LigeroProof, PoseidonSponge, DEFAULT_SECURITY_LEVEL,  # noqa: F401,E402
+                  CHACHA_SEED_BYTES)

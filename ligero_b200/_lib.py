@@ -63,6 +63,38 @@ SIGNATURES = {
     "lg_linear_test_seeded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_size_t)]),
     "lg_quadratic_test": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_size_t)]),
     "lg_open": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "lg_circuit_new": (c_int, [POINTER(c_void_p)]),
+    "lg_circuit_free": (c_int, [c_void_p]),
+    "lg_circuit_last_error": (c_char_p, [c_void_p]),
+    "lg_circuit_constant": (c_int, [c_void_p, c_void_p, POINTER(c_size_t)]),
+    "lg_circuit_new_variable": (c_int, [c_void_p, c_char_p, POINTER(c_size_t)]),
+    "lg_circuit_get_variable": (c_int, [c_void_p, c_char_p, POINTER(c_size_t)]),
+    "lg_circuit_add": (c_int, [c_void_p, c_size_t, c_size_t, POINTER(c_size_t)]),
+    "lg_circuit_mul": (c_int, [c_void_p, c_size_t, c_size_t, POINTER(c_size_t)]),
+    "lg_circuit_counts": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
+    "lg_circuit_node": (c_int, [c_void_p, c_size_t, POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t), c_void_p]),
+    "lg_circuit_evaluate": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "lg_circuit_from_r1cs": (c_int, [c_size_t, c_size_t, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                     POINTER(c_void_p), c_void_p]),
+    "lg_sponge_new": (c_int, [c_int, c_int, c_uint64, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),
+    "lg_sponge_test": (c_int, [POINTER(c_void_p)]),
+    "lg_sponge_clone": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "lg_sponge_free": (c_int, [c_void_p]),
+    "lg_sponge_absorb_bytes": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "lg_sponge_absorb_fr": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "lg_sponge_squeeze_bytes": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "lg_ligero_new": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, POINTER(c_void_p)]),
+    "lg_ligero_free": (c_int, [c_void_p]),
+    "lg_ligero_params": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t),
+                                 POINTER(c_size_t)]),
+    "lg_ligero_witness_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "lg_prove": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, POINTER(c_void_p)]),
+    "lg_prove_with_labels": (c_int, [c_void_p, POINTER(c_char_p), c_void_p, c_size_t, c_void_p, POINTER(c_void_p)]),
+    "lg_prove_matrix": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "lg_verify": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int)]),
+    "lg_proof_free": (c_int, [c_void_p]),
+    "lg_proof_serialize": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t)]),
+    "lg_proof_deserialize": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
     "lg_intt": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t]),
     "lg_bench_int_peak": (c_int, [c_void_p, c_double, POINTER(c_double), POINTER(c_double)]),
 }

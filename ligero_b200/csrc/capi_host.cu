@@ -1,0 +1,1115 @@
+// Host driver: the reference's public surface rebuilt over the device primitives.
+//   ArithmeticCircuit  (src/arithmetic_circuit/mod.rs)        -> lg_circuit_*
+//   LigeroCircuit::new (src/ligero/mod.rs:147-433)            -> lg_ligero_new
+//   LigeroCircuit::prove / prove_inner (435-578, 646-669, 712-747, 832-859, 935-955) -> lg_prove
+//   LigeroCircuit::verify (613-644, 671-708, 749-830, 861-933, 957-996)              -> lg_verify
+//   PoseidonSponge (ark-crypto-primitives; stays on the host)  -> lg_sponge_*
+// Same names, argument meaning and failure behaviour as the reference (its panics become LG_ERR_*
+// codes with the panic text in lg_last_error).  All heavy arithmetic goes through the C-ABI entry
+// points of capi.cu / capi_protocol.cu on the GPU; this file only sequences the Fiat-Shamir transcript.
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "capi_types.h"
+#include "host_field.h"
+#include "host_prng.h"
+
+using namespace lg;
+using lgh::Fq;
+
+namespace {
+
+enum NodeType : uint8_t { N_VAR = 0, N_CONST = 1, N_ADD = 2, N_MUL = 3 };
+struct Node {
+  uint8_t type;
+  uint64_t l, r;  // operands; for N_CONST l = index into const_values; for N_VAR l = index into labels
+};
+
+typedef std::array<uint8_t, 32> Digest;
+
+struct Opened {
+  std::vector<std::vector<Fq>> columns;
+  std::vector<uint64_t> leaf_index;
+  std::vector<Digest> sibling;
+  std::vector<std::vector<Digest>> auth;
+};
+
+}  // namespace
+
+struct lg_circuit {
+  std::vector<Node> nodes;
+  std::vector<Fq> const_values;
+  std::vector<std::string> labels;
+  std::map<Fq, size_t> constants;            // value -> node index
+  std::map<std::string, size_t> variables;   // label -> node index
+  std::string error;
+  size_t push(Node n) {
+    nodes.push_back(n);
+    return nodes.size() - 1;
+  }
+};
+
+struct lg_sponge {
+  lgh::PoseidonSponge s;
+  explicit lg_sponge(const lgh::PoseidonConfig& c) : s(c) {}
+};
+
+struct lg_ligero {
+  lg_ctx* ctx = nullptr;
+  lg_circuit circuit;  // formatted copy: constant 1 at node 0
+  std::vector<size_t> outputs;
+  size_t one_index = 0;
+  bool one_found = false;
+  size_t m = 0, k = 0, n = 0, t = 0, sol_len = 0;
+  lg_constraints* a = nullptr;
+};
+
+struct lg_proof {
+  Digest root;
+  std::vector<Fq> preenc_u_lc;
+  Opened interleaved;
+  std::vector<Fq> linear_poly;
+  Opened linear;
+  std::vector<Fq> quadratic_poly;
+  Opened quadratic;
+};
+
+namespace {
+
+int fail(lg_ctx* ctx, int code, const std::string& msg) { return set_error(ctx ? &ctx->c : nullptr, code, msg); }
+
+size_t bump_index(size_t one_index, bool one_found, size_t index) {  // src/ligero/mod.rs:230-242
+  if (one_found) {
+    if (index < one_index) return index + 1;
+    if (index == one_index) return 0;
+    return index;
+  }
+  return index + 1;
+}
+
+size_t calculate_t(size_t sec_param, size_t d_num, size_t d_den, size_t codeword_len) {
+  const double residual = (double)codeword_len / std::pow(2.0, 254);
+  const double rhs = std::log2(std::pow(2.0, -(double)sec_param) - residual);
+  const double nom = rhs - 1.0;
+  const double denom = std::log2(1.0 - 0.5 * (double)d_num / (double)d_den);
+  const size_t t = (size_t)std::ceil(nom / denom);
+  return t < codeword_len ? t : codeword_len;
+}
+
+// iterative version of inner_evaluate (src/arithmetic_circuit/mod.rs:247-271): same values, no recursion
+int evaluation_trace(const lg_circuit& c, const std::vector<std::pair<size_t, Fq>>& vars, const std::vector<size_t>& outputs,
+                     std::vector<Fq>& vals, std::vector<uint8_t>& set, std::string& err) {
+  const size_t N = c.nodes.size();
+  vals.assign(N, lgh::kZero);
+  set.assign(N, 0);
+  for (size_t i = 0; i < N; i++)
+    if (c.nodes[i].type == N_CONST) {
+      vals[i] = c.const_values[c.nodes[i].l];
+      set[i] = 1;
+    }
+  for (auto& v : vars) {
+    if (v.first >= N || c.nodes[v.first].type != N_VAR) {
+      err = "Value supplied for non-variable node";
+      return ERR_INVALID;
+    }
+    vals[v.first] = v.second;
+    set[v.first] = 1;
+  }
+  std::vector<size_t> stack;
+  for (size_t out : outputs) {
+    if (out >= N) {
+      err = "output node not in circuit";
+      return ERR_INVALID;
+    }
+    stack.push_back(out);
+    while (!stack.empty()) {
+      const size_t i = stack.back();
+      if (set[i]) {
+        stack.pop_back();
+        continue;
+      }
+      const Node& nd = c.nodes[i];
+      if (nd.type == N_VAR) {
+        err = "Uninitialised variable";
+        return ERR_INVALID;
+      }
+      if (!set[nd.l]) {
+        stack.push_back(nd.l);
+        continue;
+      }
+      if (!set[nd.r]) {
+        stack.push_back(nd.r);
+        continue;
+      }
+      vals[i] = nd.type == N_ADD ? lgh::add(vals[nd.l], vals[nd.r]) : lgh::mul(vals[nd.l], vals[nd.r]);
+      set[i] = 1;
+      stack.pop_back();
+    }
+  }
+  return OK;
+}
+
+// host radix-2 transform, natural order (only for the verifier's single size-2k FFT / size-k pieces)
+void host_fft(std::vector<Fq>& a, bool inverse) {
+  const size_t n = a.size();
+  int log_n = 0;
+  while (((size_t)1 << log_n) < n) log_n++;
+  for (size_t i = 0; i < n; i++) {
+    size_t j = 0;
+    for (int b = 0; b < log_n; b++) j |= ((i >> b) & 1) << (log_n - 1 - b);
+    if (i < j) std::swap(a[i], a[j]);
+  }
+  Fq w = lgh::root_of_unity(log_n);
+  if (inverse) w = lgh::inv(w);
+  std::vector<Fq> tw(n / 2 ? n / 2 : 1);
+  tw[0] = lgh::kOne;
+  for (size_t i = 1; i < tw.size(); i++) tw[i] = lgh::mul(tw[i - 1], w);
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const size_t half = len / 2, step = n / len;
+    for (size_t s = 0; s < n; s += len)
+      for (size_t j = 0; j < half; j++) {
+        const Fq u = a[s + j], v = lgh::mul(a[s + j + half], tw[j * step]);
+        a[s + j] = lgh::add(u, v);
+        a[s + j + half] = lgh::sub(u, v);
+      }
+  }
+  if (inverse) {
+    const Fq ninv = lgh::inv(lgh::from_u64(n));
+    for (auto& x : a) x = lgh::mul(x, ninv);
+  }
+}
+
+Fq poly_eval(const std::vector<Fq>& c, const Fq& x) {
+  Fq acc = lgh::kZero;
+  for (size_t i = c.size(); i-- > 0;) acc = lgh::add(lgh::mul(acc, x), c[i]);
+  return acc;
+}
+
+// ---- constraint matrix (right-hand block of A) straight into CSC ------------------------------------
+struct Triplet {
+  uint32_t col, row, vid;
+};
+
+int build_constraints(lg_ligero* L, std::string& err) {
+  const lg_circuit& c = L->circuit;
+  const auto& nodes = c.nodes;
+  const size_t mk = L->m * L->k;
+  // index_map: node -> position after dropping every constant but node 0 (mod.rs:179-194)
+  std::vector<uint32_t> index_map(nodes.size(), 0xffffffffu);
+  index_map[0] = 0;
+  size_t seen = 0;
+  for (size_t i = 1; i < nodes.size(); i++) {
+    if (nodes[i].type == N_CONST) seen++;
+    else index_map[i] = (uint32_t)(i - seen);
+  }
+  std::map<Fq, uint32_t> const_ids;
+  std::vector<Fq> table;
+  const Fq minus_one = lgh::neg(lgh::kOne);
+  auto vid_of = [&](const Fq& v) -> uint32_t {
+    if (v == lgh::kOne) return 0;
+    if (v == minus_one) return 1;
+    auto it = const_ids.find(v);
+    if (it != const_ids.end()) return it->second;
+    const uint32_t id = (uint32_t)table.size() + 2;
+    table.push_back(v);
+    const_ids[v] = id;
+    return id;
+  };
+  auto cval = [&](size_t node) { return c.const_values[nodes[node].l]; };
+  std::vector<Triplet> trip;
+  size_t row = 0;  // row inside each P matrix
+  auto add_gate = [&](size_t l, size_t r, uint32_t own_col) -> bool {  // P_add row
+    const bool lc = nodes[l].type == N_CONST, rc = nodes[r].type == N_CONST;
+    if (lc && rc) return false;
+    const uint32_t base = (uint32_t)(3 * mk + row);
+    if (lc) {
+      trip.push_back({0, base, vid_of(cval(l))});
+      trip.push_back({index_map[r], base, 0});
+    } else if (rc) {
+      trip.push_back({index_map[l], base, 0});
+      trip.push_back({0, base, vid_of(cval(r))});
+    } else {
+      trip.push_back({index_map[l], base, 0});
+      trip.push_back({index_map[r], base, 0});
+    }
+    trip.push_back({own_col, base, 1});
+    return true;
+  };
+  auto mul_gate = [&](size_t l, size_t r, uint32_t own_col) -> bool {  // rows of -P_x, -P_y, -P_z
+    const bool lc = nodes[l].type == N_CONST, rc = nodes[r].type == N_CONST;
+    if (lc && rc) return false;
+    const uint32_t rx = (uint32_t)row, ry = (uint32_t)(mk + row), rz = (uint32_t)(2 * mk + row);
+    if (lc) {
+      trip.push_back({0, rx, vid_of(lgh::neg(cval(l)))});
+      trip.push_back({index_map[r], ry, 1});
+    } else if (rc) {
+      trip.push_back({index_map[l], rx, 1});
+      trip.push_back({0, ry, vid_of(lgh::neg(cval(r)))});
+    } else {
+      trip.push_back({index_map[l], rx, 1});
+      trip.push_back({index_map[r], ry, 1});
+    }
+    trip.push_back({own_col, rz, 1});
+    return true;
+  };
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const Node& nd = nodes[i];
+    if (nd.type == N_CONST && i != 0) continue;  // constants other than node 0 get no row
+    if (row >= mk) {
+      err = "internal: more rows than m*k";
+      return ERR_STATE;
+    }
+    if (nd.type == N_ADD) {
+      if (!add_gate(nd.l, nd.r, index_map[i])) {
+        err = "Add(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:325)";
+        return ERR_UNSUPPORTED;
+      }
+    } else if (nd.type == N_MUL) {
+      if (!mul_gate(nd.l, nd.r, index_map[i])) {
+        err = "Mul(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:345)";
+        return ERR_UNSUPPORTED;
+      }
+    }
+    row++;
+  }
+  for (size_t o : L->outputs) {  // o = 1 for each output node (mod.rs:369-414)
+    const Node& nd = nodes[o];
+    if (row >= mk) {
+      err = "internal: more rows than m*k";
+      return ERR_STATE;
+    }
+    bool ok;
+    if (nd.type == N_ADD) ok = add_gate(nd.l, nd.r, 0);
+    else if (nd.type == N_MUL) ok = mul_gate(nd.l, nd.r, 0);
+    else {
+      err = "The output node must be an addition or multiplication gate";
+      return ERR_INVALID;
+    }
+    if (!ok) {
+      err = "output gate with two constant operands is not supported (the reference panics)";
+      return ERR_UNSUPPORTED;
+    }
+    row++;
+  }
+  std::stable_sort(trip.begin(), trip.end(), [](const Triplet& a, const Triplet& b) { return a.col < b.col; });
+  std::vector<uint32_t> col_ptr(mk + 1, 0), row_idx(trip.size()), val_id(trip.size());
+  for (const auto& t : trip) col_ptr[t.col + 1]++;
+  for (size_t cidx = 0; cidx < mk; cidx++) col_ptr[cidx + 1] += col_ptr[cidx];
+  for (size_t e = 0; e < trip.size(); e++) {
+    row_idx[e] = trip[e].row;
+    val_id[e] = trip[e].vid;
+  }
+  return lg_constraints_create(L->ctx, mk, col_ptr.data(), row_idx.data(), val_id.data(), trip.size(),
+                               table.empty() ? nullptr : (const uint64_t*)table.data(), table.size(), &L->a);
+}
+
+// ---- openings -----------------------------------------------------------------------------------------
+int open_columns(lg_ligero* L, lg_matrix* U, lgh::PoseidonSponge& sponge, Opened& out) {  // mod.rs:935-955
+  const std::vector<uint8_t> seed = sponge.squeeze_bytes(32);
+  std::vector<uint64_t> idx(L->t);
+  LG_TRY(lg_expand_indices(seed.data(), L->n, L->t, idx.data()));
+  const size_t rows = 4 * L->m;
+  int log_n = 0;
+  while (((size_t)1 << log_n) < L->n) log_n++;
+  const size_t depth = (size_t)(log_n - 1);
+  std::vector<Fq> cols(L->t * rows);
+  std::vector<uint8_t> sib(L->t * 32), auth(L->t * depth * 32 + 1);
+  LG_TRY(lg_open(U, idx.data(), L->t, (uint64_t*)cols.data(), sib.data(), auth.data()));
+  out.columns.resize(L->t);
+  out.leaf_index = idx;
+  out.sibling.resize(L->t);
+  out.auth.assign(L->t, std::vector<Digest>(depth));
+  for (size_t q = 0; q < L->t; q++) {
+    out.columns[q].assign(cols.begin() + q * rows, cols.begin() + (q + 1) * rows);
+    memcpy(out.sibling[q].data(), sib.data() + 32 * q, 32);
+    for (size_t d = 0; d < depth; d++) memcpy(out.auth[q][d].data(), auth.data() + 32 * (q * depth + d), 32);
+  }
+  return OK;
+}
+
+bool verify_path(const lg_ctx* ctx, const Digest& root, const Digest& leaf, const Digest& sibling, const std::vector<Digest>& auth,
+                 uint64_t index) {
+  uint8_t buf[80];
+  size_t len = 0;
+  const Digest* lr[2] = {(index & 1) ? &sibling : &leaf, (index & 1) ? &leaf : &sibling};
+  for (int s = 0; s < 2; s++) {
+    if (ctx->leaf_len_prefix) {
+      const uint64_t l = 32;
+      memcpy(buf + len, &l, 8);
+      len += 8;
+    }
+    memcpy(buf + len, lr[s]->data(), 32);
+    len += 32;
+  }
+  Digest cur;
+  lgh::sha256(buf, len, cur.data());
+  index >>= 1;
+  for (size_t d = auth.size(); d-- > 0;) {
+    uint8_t b2[64];
+    if (index & 1) {
+      memcpy(b2, auth[d].data(), 32);
+      memcpy(b2 + 32, cur.data(), 32);
+    } else {
+      memcpy(b2, cur.data(), 32);
+      memcpy(b2 + 32, auth[d].data(), 32);
+    }
+    lgh::sha256(b2, 64, cur.data());
+    index >>= 1;
+  }
+  return cur == root;
+}
+
+// verify_column_openings (mod.rs:957-996): re-derive the indices, hash the columns on the GPU, check paths
+int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::PoseidonSponge& sponge, bool* ok) {
+  *ok = false;
+  const std::vector<uint8_t> seed = sponge.squeeze_bytes(32);
+  std::vector<uint64_t> idx(L->t);
+  LG_TRY(lg_expand_indices(seed.data(), L->n, L->t, idx.data()));
+  const size_t rows = 4 * L->m;
+  if (o.columns.size() != L->t || o.leaf_index.size() != L->t || o.sibling.size() != L->t || o.auth.size() != L->t) return OK;
+  int log_n = 0;
+  while (((size_t)1 << log_n) < L->n) log_n++;
+  std::vector<Fq> flat(L->t * rows);
+  for (size_t q = 0; q < L->t; q++) {
+    if (o.columns[q].size() != rows || o.auth[q].size() != (size_t)(log_n - 1)) return OK;
+    std::copy(o.columns[q].begin(), o.columns[q].end(), flat.begin() + q * rows);
+  }
+  Ctx* c = &L->ctx->c;
+  Fr* dcols;
+  uint8_t* ddig;
+  LG_CUDA(c, cudaMalloc(&dcols, flat.size() * sizeof(Fr)));
+  LG_CUDA(c, cudaMalloc(&ddig, L->t * 32));
+  std::vector<uint8_t> dig(L->t * 32);
+  cudaMemcpyAsync(dcols, flat.data(), flat.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream);
+  int s = hash_column_list(c, dcols, rows, L->t, ddig, L->ctx->col_len_prefix);
+  cudaMemcpyAsync(dig.data(), ddig, dig.size(), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(dcols);
+  cudaFree(ddig);
+  if (s != OK) return s;
+  if (e != cudaSuccess) return set_error(c, ERR_CUDA, cudaGetErrorString(e));
+  for (size_t q = 0; q < L->t; q++) {
+    if (o.leaf_index[q] != idx[q]) return OK;
+    Digest leaf;
+    memcpy(leaf.data(), dig.data() + 32 * q, 32);
+    if (!verify_path(L->ctx, root, leaf, o.sibling[q], o.auth[q], idx[q])) return OK;
+  }
+  *ok = true;
+  return OK;
+}
+
+// ---- serialisation (arkworks CanonicalSerialize-compatible layout; the reference defines none) -------
+void put_u64(std::vector<uint8_t>& b, uint64_t v) {
+  for (int i = 0; i < 8; i++) b.push_back((uint8_t)(v >> (8 * i)));
+}
+void put_fr(std::vector<uint8_t>& b, const Fq& x) {
+  const Fq c = lgh::from_mont(x);
+  const uint8_t* p = (const uint8_t*)c.l;
+  b.insert(b.end(), p, p + 32);
+}
+void put_frs(std::vector<uint8_t>& b, const std::vector<Fq>& v) {
+  put_u64(b, v.size());
+  for (auto& x : v) put_fr(b, x);
+}
+void put_digest(std::vector<uint8_t>& b, const Digest& d) {
+  put_u64(b, 32);
+  b.insert(b.end(), d.begin(), d.end());
+}
+void put_opened(std::vector<uint8_t>& b, const Opened& o) {
+  put_u64(b, o.columns.size());
+  for (auto& col : o.columns) put_frs(b, col);
+  put_u64(b, o.leaf_index.size());
+  for (size_t q = 0; q < o.leaf_index.size(); q++) {  // Path { leaf_sibling_hash, auth_path, leaf_index }
+    put_digest(b, o.sibling[q]);
+    put_u64(b, o.auth[q].size());
+    for (auto& d : o.auth[q]) put_digest(b, d);
+    put_u64(b, o.leaf_index[q]);
+  }
+}
+struct Reader {
+  const uint8_t* p;
+  size_t len, pos = 0;
+  bool ok = true;
+  uint64_t u64() {
+    if (pos + 8 > len) {
+      ok = false;
+      return 0;
+    }
+    uint64_t v;
+    memcpy(&v, p + pos, 8);
+    pos += 8;
+    return v;
+  }
+  Fq fr() {
+    Fq c = lgh::kZero;
+    if (pos + 32 > len) {
+      ok = false;
+      return c;
+    }
+    memcpy(c.l, p + pos, 32);
+    pos += 32;
+    if (lgh::geq_p(c.l)) {
+      ok = false;
+      return lgh::kZero;
+    }
+    return lgh::to_mont(c);
+  }
+  std::vector<Fq> frs() {
+    const uint64_t n = u64();
+    std::vector<Fq> v;
+    if (!ok || n > (len - pos) / 32) {
+      ok = false;
+      return v;
+    }
+    v.reserve(n);
+    for (uint64_t i = 0; i < n && ok; i++) v.push_back(fr());
+    return v;
+  }
+  Digest digest() {
+    Digest d{};
+    if (u64() != 32 || pos + 32 > len) {
+      ok = false;
+      return d;
+    }
+    memcpy(d.data(), p + pos, 32);
+    pos += 32;
+    return d;
+  }
+  Opened opened() {
+    Opened o;
+    uint64_t nc = u64();
+    if (!ok || nc > len) {
+      ok = false;
+      return o;
+    }
+    for (uint64_t i = 0; i < nc && ok; i++) o.columns.push_back(frs());
+    uint64_t np = u64();
+    if (!ok || np > len) {
+      ok = false;
+      return o;
+    }
+    for (uint64_t i = 0; i < np && ok; i++) {
+      o.sibling.push_back(digest());
+      uint64_t na = u64();
+      if (!ok || na > len) {
+        ok = false;
+        return o;
+      }
+      std::vector<Digest> a;
+      for (uint64_t j = 0; j < na && ok; j++) a.push_back(digest());
+      o.auth.push_back(a);
+      o.leaf_index.push_back(u64());
+    }
+    return o;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------
+// ArithmeticCircuit
+// ---------------------------------------------------------------------------------------------------
+int lg_circuit_new(lg_circuit** out) {
+  if (!out) return ERR_INVALID;
+  *out = new (std::nothrow) lg_circuit();
+  return *out ? OK : ERR_NOMEM;
+}
+int lg_circuit_free(lg_circuit* c) {
+  delete c;
+  return OK;
+}
+const char* lg_circuit_last_error(const lg_circuit* c) { return c ? c->error.c_str() : "null circuit"; }
+
+int lg_circuit_constant(lg_circuit* c, const uint64_t value[4], size_t* index_out) {  // mod.rs:76-84
+  if (!c || !value) return ERR_INVALID;
+  Fq v;
+  memcpy(v.l, value, 32);
+  auto it = c->constants.find(v);
+  size_t idx;
+  if (it != c->constants.end()) {
+    idx = it->second;
+  } else {
+    c->const_values.push_back(v);
+    idx = c->push({N_CONST, c->const_values.size() - 1, 0});
+    c->constants[v] = idx;
+  }
+  if (index_out) *index_out = idx;
+  return OK;
+}
+
+int lg_circuit_new_variable(lg_circuit* c, const char* label, size_t* index_out) {  // mod.rs:92-109
+  if (!c) return ERR_INVALID;
+  const std::string lab = label ? std::string(label) : "var_" + std::to_string(c->variables.size());
+  if (c->variables.count(lab)) {
+    c->error = "Variable label already in use: " + lab;
+    return ERR_INVALID;
+  }
+  c->labels.push_back(lab);
+  const size_t idx = c->push({N_VAR, c->labels.size() - 1, 0});
+  c->variables[lab] = idx;
+  if (index_out) *index_out = idx;
+  return OK;
+}
+
+int lg_circuit_get_variable(const lg_circuit* c, const char* label, size_t* index_out) {
+  if (!c || !label || !index_out) return ERR_INVALID;
+  auto it = c->variables.find(label);
+  if (it == c->variables.end()) return ERR_INVALID;  // "Variable not in circuit"
+  *index_out = it->second;
+  return OK;
+}
+
+static int push_gate(lg_circuit* c, uint8_t type, size_t l, size_t r, size_t* index_out) {  // mod.rs:125-145
+  if (!c) return ERR_INVALID;
+  if (l >= c->nodes.size() || r >= c->nodes.size()) {
+    c->error = type == N_ADD ? "operand to Add not in circuit" : "operand to Mul not in circuit";
+    return ERR_INVALID;
+  }
+  const size_t idx = c->push({type, l, r});
+  if (index_out) *index_out = idx;
+  return OK;
+}
+int lg_circuit_add(lg_circuit* c, size_t l, size_t r, size_t* index_out) { return push_gate(c, N_ADD, l, r, index_out); }
+int lg_circuit_mul(lg_circuit* c, size_t l, size_t r, size_t* index_out) { return push_gate(c, N_MUL, l, r, index_out); }
+
+int lg_circuit_counts(const lg_circuit* c, size_t* nodes, size_t* constants, size_t* variables, size_t* gates) {
+  if (!c) return ERR_INVALID;
+  if (nodes) *nodes = c->nodes.size();
+  if (constants) *constants = c->constants.size();
+  if (variables) *variables = c->variables.size();
+  if (gates) {
+    size_t g = 0;
+    for (auto& n : c->nodes) g += (n.type == N_ADD || n.type == N_MUL);
+    *gates = g;
+  }
+  return OK;
+}
+
+int lg_circuit_node(const lg_circuit* c, size_t index, int* type, size_t* left, size_t* right, uint64_t value[4]) {
+  if (!c || index >= c->nodes.size()) return ERR_INVALID;
+  const Node& n = c->nodes[index];
+  if (type) *type = n.type;
+  if (left) *left = (n.type == N_ADD || n.type == N_MUL) ? n.l : 0;
+  if (right) *right = (n.type == N_ADD || n.type == N_MUL) ? n.r : 0;
+  if (value && n.type == N_CONST) memcpy(value, c->const_values[n.l].l, 32);
+  return OK;
+}
+
+// evaluation_trace_multioutput + evaluate_multioutput (mod.rs:325-400): values of the output nodes
+int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
+                        size_t n_outputs, uint64_t* out_vals) {
+  if (!c || (n_vars && (!var_idx || !var_vals)) || !outputs || !out_vals) return ERR_INVALID;
+  std::vector<std::pair<size_t, Fq>> vars(n_vars);
+  for (size_t i = 0; i < n_vars; i++) {
+    vars[i].first = var_idx[i];
+    memcpy(vars[i].second.l, var_vals + 4 * i, 32);
+  }
+  std::vector<Fq> vals;
+  std::vector<uint8_t> set;
+  std::string err;
+  const std::vector<size_t> outs(outputs, outputs + n_outputs);
+  int s = evaluation_trace(*c, vars, outs, vals, set, err);
+  if (s != OK) {
+    const_cast<lg_circuit*>(c)->error = err;
+    return s;
+  }
+  for (size_t i = 0; i < n_outputs; i++) memcpy(out_vals + 4 * i, vals[outputs[i]].l, 32);
+  return OK;
+}
+
+// from_constraint_system (mod.rs:455-520).  Matrices as ConstraintSystem::to_matrices yields them: CSR with
+// coefficient Fr values and column indices (column 0 = the constant one), n_cols = instance + witness variables.
+int lg_circuit_from_r1cs(size_t n_constraints, size_t n_cols, const uint64_t* const row_ptr[3], const uint64_t* const col_idx[3],
+                         const uint64_t* const coeffs[3], lg_circuit** out, size_t* outputs) {
+  if (!out || !outputs || !row_ptr || !col_idx || !coeffs || n_cols == 0) return ERR_INVALID;
+  lg_circuit* c = new (std::nothrow) lg_circuit();
+  if (!c) return ERR_NOMEM;
+  size_t one;
+  lg_circuit_constant(c, lgh::kOne.l, &one);
+  for (size_t i = 1; i < n_cols; i++) lg_circuit_new_variable(c, nullptr, nullptr);
+  std::vector<size_t> rows[3];
+  for (int mtx = 0; mtx < 3; mtx++) {
+    for (size_t r = 0; r < n_constraints; r++) {  // compile_sparse_scalar_product (501-520)
+      std::vector<std::pair<size_t, size_t>> consts;
+      for (uint64_t e = row_ptr[mtx][r]; e < row_ptr[mtx][r + 1]; e++) {
+        size_t ci;
+        lg_circuit_constant(c, coeffs[mtx] + 4 * e, &ci);
+        consts.push_back({ci, (size_t)col_idx[mtx][e]});
+      }
+      if (consts.empty()) {  // add_nodes(empty).reduce().unwrap() panics in the reference
+        delete c;
+        return ERR_INVALID;
+      }
+      std::vector<size_t> products;
+      for (auto& cv : consts) {
+        if (cv.second >= n_cols) {
+          delete c;
+          return ERR_INVALID;
+        }
+        if (cv.first == 0 || cv.second == 0) products.push_back(cv.first + cv.second);
+        else {
+          size_t p;
+          lg_circuit_mul(c, cv.first, cv.second, &p);
+          products.push_back(p);
+        }
+      }
+      size_t acc = products[0];
+      for (size_t i = 1; i < products.size(); i++) lg_circuit_add(c, acc, products[i], &acc);
+      rows[mtx].push_back(acc);
+    }
+  }
+  std::vector<size_t> ab(n_constraints), mc(n_constraints);
+  for (size_t r = 0; r < n_constraints; r++) lg_circuit_mul(c, rows[0][r], rows[1][r], &ab[r]);
+  size_t minus_one;
+  const Fq m1 = lgh::neg(lgh::kOne);
+  lg_circuit_constant(c, m1.l, &minus_one);
+  for (size_t r = 0; r < n_constraints; r++) lg_circuit_mul(c, rows[2][r], minus_one, &mc[r]);
+  for (size_t r = 0; r < n_constraints; r++) {
+    size_t a1, a2;
+    lg_circuit_add(c, ab[r], mc[r], &a1);
+    lg_circuit_add(c, a1, one, &a2);
+    outputs[r] = a2;
+  }
+  *out = c;
+  return OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sponge
+// ---------------------------------------------------------------------------------------------------
+int lg_sponge_new(int full_rounds, int partial_rounds, uint64_t alpha, const uint64_t* mds, const uint64_t* ark, int rate, int capacity,
+                  lg_sponge** out) {
+  if (!out || !mds || !ark || rate < 1 || capacity < 0 || full_rounds < 0 || partial_rounds < 0) return ERR_INVALID;
+  lgh::PoseidonConfig cfg;
+  cfg.full_rounds = full_rounds;
+  cfg.partial_rounds = partial_rounds;
+  cfg.alpha = alpha;
+  cfg.rate = rate;
+  cfg.capacity = capacity;
+  const size_t t = (size_t)rate + capacity;
+  cfg.mds.resize(t * t);
+  cfg.ark.resize((size_t)(full_rounds + partial_rounds) * t);
+  memcpy(cfg.mds.data(), mds, cfg.mds.size() * 32);
+  memcpy(cfg.ark.data(), ark, cfg.ark.size() * 32);
+  *out = new (std::nothrow) lg_sponge(cfg);
+  return *out ? OK : ERR_NOMEM;
+}
+
+// ark_poly_commit::test_sponge() with the deterministic ark_std::test_rng() (ChaCha12 from the fixed seed)
+int lg_sponge_test(lg_sponge** out) {
+  if (!out) return ERR_INVALID;
+  const uint8_t seed[32] = {1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0};
+  ChaChaRng rng(seed, 12);
+  lgh::PoseidonConfig cfg;
+  cfg.full_rounds = 8;
+  cfg.partial_rounds = 31;
+  cfg.alpha = 17;
+  cfg.rate = 2;
+  cfg.capacity = 1;
+  const Fq one = lgh::kOne, zero = lgh::kZero;
+  cfg.mds = {one, zero, one, one, one, zero, zero, one, one};
+  for (int i = 0; i < (8 + 31) * 3; i++) {
+    const Fr e = fr_rand(rng);
+    Fq q;
+    memcpy(q.l, e.v, 32);
+    cfg.ark.push_back(q);
+  }
+  *out = new (std::nothrow) lg_sponge(cfg);
+  return *out ? OK : ERR_NOMEM;
+}
+int lg_sponge_clone(const lg_sponge* s, lg_sponge** out) {
+  if (!s || !out) return ERR_INVALID;
+  *out = new (std::nothrow) lg_sponge(*s);
+  return *out ? OK : ERR_NOMEM;
+}
+int lg_sponge_free(lg_sponge* s) {
+  delete s;
+  return OK;
+}
+int lg_sponge_absorb_bytes(lg_sponge* s, const uint8_t* data, size_t len) {
+  if (!s || (!data && len)) return ERR_INVALID;
+  s->s.absorb_bytes(data, len);
+  return OK;
+}
+int lg_sponge_absorb_fr(lg_sponge* s, const uint64_t* elems, size_t count) {
+  if (!s || (!elems && count)) return ERR_INVALID;
+  std::vector<Fq> v(count);
+  memcpy(v.data(), elems, count * 32);
+  s->s.absorb_field(v);
+  return OK;
+}
+int lg_sponge_squeeze_bytes(lg_sponge* s, uint8_t* out, size_t len) {
+  if (!s || !out) return ERR_INVALID;
+  const std::vector<uint8_t> b = s->s.squeeze_bytes(len);
+  memcpy(out, b.data(), len);
+  return OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LigeroCircuit
+// ---------------------------------------------------------------------------------------------------
+int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_ligero** out) {
+  if (!ctx || !circuit || !out || (!outputs && n_outputs)) return ERR_INVALID;
+  if (circuit->nodes.empty()) return fail(ctx, ERR_INVALID, "empty circuit");
+  lg_ligero* L = new (std::nothrow) lg_ligero();
+  if (!L) return ERR_NOMEM;
+  L->ctx = ctx;
+  L->circuit = *circuit;
+  lg_circuit& c = L->circuit;
+  auto it = c.constants.find(lgh::kOne);
+  if (it != c.constants.end()) {
+    L->one_index = it->second;
+    L->one_found = true;
+  } else {
+    L->one_index = 1;
+    L->one_found = false;
+  }
+  const size_t oi = L->one_index;
+  const bool of = L->one_found;
+  if (oi != 0) {  // insert_one (mod.rs:244-271)
+    if (of) {
+      c.nodes.erase(c.nodes.begin() + oi);
+    } else {
+      c.const_values.push_back(lgh::kOne);
+    }
+    Node one_node{N_CONST, 0, 0};
+    if (of) {
+      // keep the existing const_values slot of the constant 1
+      for (size_t j = 0; j < c.const_values.size(); j++)
+        if (c.const_values[j] == lgh::kOne) one_node.l = j;
+    } else {
+      one_node.l = c.const_values.size() - 1;
+    }
+    c.nodes.insert(c.nodes.begin(), one_node);
+    for (auto& nd : c.nodes)
+      if (nd.type == N_ADD || nd.type == N_MUL) {
+        nd.l = bump_index(oi, of, nd.l);
+        nd.r = bump_index(oi, of, nd.r);
+      }
+    for (auto& kv : c.constants) kv.second = bump_index(oi, of, kv.second);
+    c.constants[lgh::kOne] = 0;
+    for (auto& kv : c.variables) kv.second = bump_index(oi, of, kv.second);
+  }
+  L->sol_len = 1 + c.nodes.size() - c.constants.size() + n_outputs;  // mod.rs:171
+  L->m = (size_t)std::ceil(std::sqrt((double)L->sol_len));             // compute_dimensions 275-279
+  size_t k = 1;
+  while (k < L->m) k <<= 1;
+  L->k = k;
+  L->n = 8 * k;                                                        // reed_solomon_parameters 283-294
+  L->t = calculate_t(lambda, L->n - k + 1, L->n, L->n);
+  if (k < 2) {
+    delete L;
+    return fail(ctx, ERR_UNSUPPORTED, "k < 2 is not supported by the device path");
+  }
+  for (size_t i = 0; i < n_outputs; i++) {
+    const size_t o = bump_index(oi, of, outputs[i]);
+    if (o >= c.nodes.size()) {
+      delete L;
+      return fail(ctx, ERR_INVALID, "output node not in circuit");
+    }
+    L->outputs.push_back(o);
+  }
+  std::string err;
+  int s = build_constraints(L, err);
+  if (s != OK) {
+    if (!err.empty()) fail(ctx, s, err);
+    lg_ligero_free(L);
+    return s;
+  }
+  *out = L;
+  return OK;
+}
+
+int lg_ligero_free(lg_ligero* L) {
+  if (!L) return OK;
+  if (L->a) lg_constraints_free(L->a);
+  delete L;
+  return OK;
+}
+
+int lg_ligero_params(const lg_ligero* L, size_t* m, size_t* k, size_t* n, size_t* t, size_t* sol_len) {
+  if (!L) return ERR_INVALID;
+  if (m) *m = L->m;
+  if (k) *k = L->k;
+  if (n) *n = L->n;
+  if (t) *t = L->t;
+  if (sol_len) *sol_len = L->sol_len;
+  return OK;
+}
+
+// the pre-encoding matrix [X;Y;Z;W] (mod.rs:476-516); out: Fr[4*m*k] host
+int lg_ligero_witness_matrix(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, uint64_t* out) {
+  if (!L || !out || (n_vars && (!var_idx || !var_vals))) return ERR_INVALID;
+  const lg_circuit& c = L->circuit;
+  std::vector<std::pair<size_t, Fq>> vars(n_vars);
+  for (size_t i = 0; i < n_vars; i++) {
+    vars[i].first = bump ? bump_index(L->one_index, L->one_found, var_idx[i]) : var_idx[i];
+    memcpy(vars[i].second.l, var_vals + 4 * i, 32);
+  }
+  std::vector<Fq> sol;
+  std::vector<uint8_t> set;
+  std::string err;
+  int s = evaluation_trace(c, vars, L->outputs, sol, set, err);
+  if (s != OK) return fail(L->ctx, s, err);
+  for (size_t i = 0; i < sol.size(); i++)
+    if (!set[i])
+      return fail(L->ctx, ERR_INVALID,
+                  "Uninitialised variable. Make sure the circuit only contains nodes upon which the final output truly depends");
+  const size_t mk = L->m * L->k;
+  Fq* X = (Fq*)out;
+  memset(X, 0, 4 * mk * sizeof(Fq));
+  Fq *Y = X + mk, *Z = Y + mk, *W = Z + mk;
+  size_t pos = 0;
+  for (size_t i = 0; i < c.nodes.size(); i++) {
+    const Node& nd = c.nodes[i];
+    if (nd.type == N_CONST && i != 0) continue;
+    if (pos >= mk) return fail(L->ctx, ERR_STATE, "internal: witness longer than m*k");
+    W[pos] = sol[i];
+    if (nd.type == N_MUL) {
+      X[pos] = sol[nd.l];
+      Y[pos] = sol[nd.r];
+      Z[pos] = sol[i];
+    }
+    pos++;
+  }
+  return OK;
+}
+
+// prove_inner on a ready pre-encoding matrix (host or device): the commit-and-test transcript
+int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, lg_proof** out) {
+  if (!L || !preenc_u || !sponge || !out) return ERR_INVALID;
+  lg_ctx* ctx = L->ctx;
+  lgh::PoseidonSponge& sp = sponge->s;
+  const size_t rows = 4 * L->m, k = L->k;
+  lg_proof* P = new (std::nothrow) lg_proof();
+  if (!P) return ERR_NOMEM;
+  lg_matrix* U = nullptr;
+  int s = lg_commit(ctx, preenc_u, rows, k, 8, P->root.data(), &U);  // mod.rs:521-551
+  auto done = [&](int code) {
+    if (U) lg_matrix_free(U);
+    if (code != OK) {
+      delete P;
+    } else {
+      *out = P;
+    }
+    return code;
+  };
+  if (s != OK) return done(s);
+  sp.absorb_bytes(P->root.data(), 32);  // 560
+  // Test-Interleaved (646-669)
+  std::vector<uint8_t> seed = sp.squeeze_bytes(32);
+  std::vector<Fq> r(rows);
+  if ((s = lg_expand_fr(ctx, seed.data(), rows, (uint64_t*)r.data())) != OK) return done(s);
+  P->preenc_u_lc.resize(k);
+  if ((s = lg_row_combine(U, (const uint64_t*)r.data(), (uint64_t*)P->preenc_u_lc.data())) != OK) return done(s);
+  sp.absorb_field(P->preenc_u_lc);
+  if ((s = open_columns(L, U, sp, P->interleaved)) != OK) return done(s);
+  // Test-Linear-Constraints (712-747)
+  seed = sp.squeeze_bytes(32);
+  std::vector<Fq> poly(2 * k);
+  size_t len = 0;
+  if ((s = lg_linear_test_seeded(U, L->a, seed.data(), (uint64_t*)poly.data(), &len)) != OK) return done(s);
+  P->linear_poly.assign(poly.begin(), poly.begin() + len);
+  sp.absorb_field(P->linear_poly);
+  if ((s = open_columns(L, U, sp, P->linear)) != OK) return done(s);
+  // Test-Quadratic-Constraints (832-859)
+  seed = sp.squeeze_bytes(32);
+  std::vector<Fq> rq(L->m);
+  if ((s = lg_expand_fr(ctx, seed.data(), L->m, (uint64_t*)rq.data())) != OK) return done(s);
+  if ((s = lg_quadratic_test(U, (const uint64_t*)rq.data(), (uint64_t*)poly.data(), &len)) != OK) return done(s);
+  P->quadratic_poly.assign(poly.begin(), poly.begin() + len);
+  sp.absorb_field(P->quadratic_poly);
+  if ((s = open_columns(L, U, sp, P->quadratic)) != OK) return done(s);
+  return done(OK);
+}
+
+// LigeroCircuit::prove (bump = 1: indices refer to the caller's circuit) / prove_inner (bump = 0)
+int lg_prove(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out) {
+  if (!L || !sponge || !out) return ERR_INVALID;
+  std::vector<Fq> pre(4 * L->m * L->k);
+  LG_TRY(lg_ligero_witness_matrix(L, var_idx, var_vals, n_vars, bump, (uint64_t*)pre.data()));
+  return lg_prove_matrix(L, (const uint64_t*)pre.data(), sponge, out);
+}
+
+int lg_prove_with_labels(lg_ligero* L, const char* const* labels, const uint64_t* var_vals, size_t n_vars, lg_sponge* sponge,
+                         lg_proof** out) {
+  if (!L || (!labels && n_vars)) return ERR_INVALID;
+  std::vector<size_t> idx(n_vars);
+  for (size_t i = 0; i < n_vars; i++) {
+    auto it = L->circuit.variables.find(labels[i]);
+    if (it == L->circuit.variables.end()) return fail(L->ctx, ERR_INVALID, std::string("Variable not found: ") + labels[i]);
+    idx[i] = it->second;
+  }
+  return lg_prove(L, idx.data(), var_vals, n_vars, 0, sponge, out);
+}
+
+int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted) {
+  if (!L || !P || !sponge || !accepted) return ERR_INVALID;
+  *accepted = 0;
+  lg_ctx* ctx = L->ctx;
+  Ctx* c = &ctx->c;
+  lgh::PoseidonSponge& sp = sponge->s;
+  const size_t m = L->m, k = L->k, n = L->n, rows = 4 * m;
+  int log_k = 0;
+  while (((size_t)1 << log_k) < k) log_k++;
+  sp.absorb_bytes(P->root.data(), 32);
+  // ---- verify_interleaved (671-708)
+  std::vector<uint8_t> seed = sp.squeeze_bytes(32);
+  std::vector<Fq> r(rows);
+  LG_TRY(lg_expand_fr(ctx, seed.data(), rows, (uint64_t*)r.data()));
+  sp.absorb_field(P->preenc_u_lc);
+  bool ok;
+  LG_TRY(verify_openings(L, P->interleaved, P->root, sp, &ok));
+  if (!ok) return OK;
+  {
+    std::vector<Fq> msg(P->preenc_u_lc);  // reed_solomon_interpolate: msg.resize(k) pads or truncates (998-1002)
+    msg.resize(k, lgh::kZero);
+    lg_matrix* W = nullptr;
+    LG_TRY(lg_encode(ctx, (const uint64_t*)msg.data(), 1, k, 8, &W));  // reed_solomon(preenc_u_lc)
+    std::vector<Fq> w(n);
+    int s = lg_matrix_read_rows(W, 0, 1, (uint64_t*)w.data());
+    lg_matrix_free(W);
+    if (s != OK) return s;
+    for (size_t q = 0; q < L->t; q++) {
+      Fq acc = lgh::kZero;
+      for (size_t i = 0; i < rows; i++) acc = lgh::add(acc, lgh::mul(r[i], P->interleaved.columns[q][i]));
+      if (w[P->interleaved.leaf_index[q]] != acc) return OK;
+    }
+  }
+  // ---- verify_linear (749-830)
+  seed = sp.squeeze_bytes(32);
+  lg_matrix* RA = nullptr;  // r_polys evaluated on the whole large domain (816-819), resident on the device
+  {
+    Fr* ra;
+    LG_CUDA(c, cudaMalloc(&ra, 4 * m * k * sizeof(Fr)));
+    int s = expand_fr(c, seed.data(), 4 * m * k, ra);
+    if (s == OK) s = lg_sparse_row_mul(ctx, L->a, (const uint64_t*)ra, (uint64_t*)ra);
+    if (s == OK) s = lg_encode(ctx, (const uint64_t*)ra, rows, k, 8, &RA);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(ra);
+    if (s != OK) return s;
+  }
+  auto free_ra = [&]() {
+    if (RA) lg_matrix_free(RA);
+    RA = nullptr;
+  };
+  const std::vector<Fq>& ql = P->linear_poly;
+  const size_t deg_l = ql.empty() ? 0 : ql.size() - 1;
+  if (deg_l >= 2 * k - 1) {
+    free_ra();
+    return OK;
+  }
+  std::vector<Fq> ie(ql);
+  ie.resize(2 * k, lgh::kZero);
+  host_fft(ie, false);
+  const size_t cof = n / (2 * k);
+  {
+    Fq sum = lgh::kZero;
+    for (size_t i = 0; i < 2 * k; i += 2) sum = lgh::add(sum, ie[i]);
+    if (!sum.is_zero()) {
+      free_ra();
+      return OK;
+    }
+  }
+  sp.absorb_field(ql);
+  {
+    int s = verify_openings(L, P->linear, P->root, sp, &ok);
+    if (s != OK || !ok) {
+      free_ra();
+      return s;
+    }
+    std::vector<Fq> rcols(L->t * rows);
+    s = lg_open(RA, P->linear.leaf_index.data(), L->t, (uint64_t*)rcols.data(), nullptr, nullptr);
+    free_ra();
+    if (s != OK) return s;
+    const Fq g = lgh::root_of_unity(log_k + 3);
+    for (size_t q = 0; q < L->t; q++) {
+      const uint64_t j = P->linear.leaf_index[q];
+      const Fq ev = (j % cof == 0) ? ie[j / cof] : poly_eval(ql, lgh::pow_u64(g, j));
+      Fq acc = lgh::kZero;
+      for (size_t i = 0; i < rows; i++) acc = lgh::add(acc, lgh::mul(rcols[q * rows + i], P->linear.columns[q][i]));
+      if (acc != ev) return OK;
+    }
+  }
+  // ---- verify_quadratic_constraints (861-933)
+  seed = sp.squeeze_bytes(32);
+  std::vector<Fq> rq(m);
+  LG_TRY(lg_expand_fr(ctx, seed.data(), m, (uint64_t*)rq.data()));
+  const std::vector<Fq>& qq = P->quadratic_poly;
+  const size_t deg_q = qq.empty() ? 0 : qq.size() - 1;
+  if (deg_q >= 2 * k - 1) return OK;
+  std::vector<Fq> iq(qq);
+  iq.resize(2 * k, lgh::kZero);
+  host_fft(iq, false);
+  for (size_t cc = 0; cc < k; cc++)
+    if (!iq[2 * cc].is_zero()) return OK;
+  sp.absorb_field(qq);
+  LG_TRY(verify_openings(L, P->quadratic, P->root, sp, &ok));
+  if (!ok) return OK;
+  {
+    const Fq g = lgh::root_of_unity(log_k + 3);
+    for (size_t q = 0; q < L->t; q++) {
+      const uint64_t j = P->quadratic.leaf_index[q];
+      const std::vector<Fq>& col = P->quadratic.columns[q];
+      const Fq lhs = (j % cof == 0) ? iq[j / cof] : poly_eval(qq, lgh::pow_u64(g, j));
+      Fq rhs = lgh::kZero;
+      for (size_t i = 0; i < m; i++) rhs = lgh::add(rhs, lgh::mul(rq[i], lgh::sub(lgh::mul(col[i], col[i + m]), col[i + 2 * m])));
+      if (lhs != rhs) return OK;
+    }
+  }
+  *accepted = 1;
+  return OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// proof container
+// ---------------------------------------------------------------------------------------------------
+int lg_proof_free(lg_proof* p) {
+  delete p;
+  return OK;
+}
+int lg_proof_serialize(const lg_proof* P, uint8_t* buf, size_t cap, size_t* len_out) {
+  if (!P || !len_out) return ERR_INVALID;
+  std::vector<uint8_t> b;
+  put_digest(b, P->root);
+  put_frs(b, P->preenc_u_lc);
+  put_opened(b, P->interleaved);
+  put_frs(b, P->linear_poly);
+  put_opened(b, P->linear);
+  put_frs(b, P->quadratic_poly);
+  put_opened(b, P->quadratic);
+  *len_out = b.size();
+  if (buf) {
+    if (cap < b.size()) return ERR_INVALID;
+    memcpy(buf, b.data(), b.size());
+  }
+  return OK;
+}
+int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out) {
+  if (!buf || !out) return ERR_INVALID;
+  Reader rd{buf, len};
+  lg_proof* P = new (std::nothrow) lg_proof();
+  if (!P) return ERR_NOMEM;
+  P->root = rd.digest();
+  P->preenc_u_lc = rd.frs();
+  P->interleaved = rd.opened();
+  P->linear_poly = rd.frs();
+  P->linear = rd.opened();
+  P->quadratic_poly = rd.frs();
+  P->quadratic = rd.opened();
+  if (!rd.ok || rd.pos != len) {
+    delete P;
+    return ERR_INVALID;
+  }
+  *out = P;
+  return OK;
+}
+
+}  // extern "C"
