@@ -165,10 +165,72 @@ static int stage_input(lg_ctx* ctx, const uint64_t* src, size_t elems, const Fr*
   return OK;
 }
 
+// Host input: upload row tiles on a copy stream while the previous tile is being encoded.  Every tile is
+// encoded with an OutMap that drops its rows at their final position in the plane layout, so no tile ever
+// needs a second pass.  (Pinned host memory makes the copies truly asynchronous; pageable memory still works.)
+static int encode_host_pipelined(lg_matrix* h, const uint64_t* host) {
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  const size_t row_bytes = m.k * sizeof(Fr);
+  size_t tile_rows = ((size_t)256 << 20) / row_bytes;
+  if (tile_rows < 1) tile_rows = 1;
+  if (tile_rows > m.rows) tile_rows = m.rows;
+  const size_t tile_bytes = tile_rows * row_bytes;
+  if (!c->copy_stream) {
+    LG_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+      LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+    }
+  }
+  if (c->stage_bytes < tile_bytes) {
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; i++) {
+      if (c->stage[i]) cudaFree(c->stage[i]);
+      c->stage[i] = nullptr;
+      LG_CUDA(c, cudaMalloc(&c->stage[i], tile_bytes));
+    }
+    c->stage_bytes = tile_bytes;
+  }
+  const size_t cos_bytes = m.log_k > 10 ? (size_t)(m.rho_inv - 1) * tile_bytes : 0;
+  if (c->tile_cosets_bytes < cos_bytes) {
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->tile_cosets) cudaFree(c->tile_cosets);
+    c->tile_cosets = nullptr;
+    LG_CUDA(c, cudaMalloc(&c->tile_cosets, cos_bytes));
+    c->tile_cosets_bytes = cos_bytes;
+  }
+  OutMap map{};
+  map.base[0] = m.u;
+  map.log_kg = m.log_k;
+  map.rows_total = m.rows;
+  // the copy stream must not overwrite a staging tile that an earlier call is still reading
+  LG_CUDA(c, cudaEventRecord(c->ev_consumed[0], c->stream));
+  LG_CUDA(c, cudaEventRecord(c->ev_consumed[1], c->stream));
+  int t = 0;
+  for (size_t row0 = 0; row0 < m.rows; row0 += tile_rows, t++) {
+    const size_t nr = row0 + tile_rows <= m.rows ? tile_rows : m.rows - row0;
+    const int b = t & 1;
+    LG_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+    LG_CUDA(c, cudaMemcpyAsync(c->stage[b], (const uint8_t*)host + row0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice,
+                               c->copy_stream));
+    LG_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    LG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    map.m = map.m_g = (uint32_t)nr;  // one block: grow(i) = row0 + i
+    map.i0 = (uint32_t)row0;
+    LG_TRY(encode_rows(c, (const Fr*)c->stage[b], nr, m.log_k, m.rho_inv, nullptr, (Fr*)c->tile_cosets, &map));
+    LG_CUDA(c, cudaEventRecord(c->ev_consumed[b], c->stream));
+  }
+  return OK;
+}
+
 static int do_encode(lg_matrix* h, const uint64_t* preenc_u) {
   Matrix& m = h->m;
   Ctx* c = m.ctx;
   if (!preenc_u) return set_error(c, ERR_INVALID, "null input matrix");
+  if (!is_device_ptr(preenc_u) && m.rows * m.k * sizeof(Fr) >= ((size_t)64 << 20) && m.rows < ((size_t)1 << 31))
+    return encode_host_pipelined(h, preenc_u);
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(h->owner, preenc_u, m.rows * m.k, &dev, &to_free));
@@ -234,6 +296,16 @@ int lg_ctx_destroy(lg_ctx* ctx) {
     cudaFree(kv.second.scale);
   }
   if (ctx->c.scratch) cudaFree(ctx->c.scratch);
+  if (ctx->c.copy_stream) {
+    cudaStreamSynchronize(ctx->c.copy_stream);
+    for (int i = 0; i < 2; i++) {
+      if (ctx->c.stage[i]) cudaFree(ctx->c.stage[i]);
+      if (ctx->c.ev_copied[i]) cudaEventDestroy(ctx->c.ev_copied[i]);
+      if (ctx->c.ev_consumed[i]) cudaEventDestroy(ctx->c.ev_consumed[i]);
+    }
+    if (ctx->c.tile_cosets) cudaFree(ctx->c.tile_cosets);
+    cudaStreamDestroy(ctx->c.copy_stream);
+  }
   for (auto& m : ctx->c.marks) cudaEventDestroy(m.second);
   for (auto& e : ctx->c.event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->c.stream);

@@ -56,6 +56,14 @@ struct Ctx {
   // scratch reused across calls
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // host-input pipeline: a copy stream, two staging tiles and the coset intermediate of one tile, so the
+  // H2D upload of row tile i+1 overlaps the encoding of tile i
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  void* tile_cosets = nullptr;
+  size_t tile_cosets_bytes = 0;
   // optional per-phase device timing (CUDA events on `stream`): bench.py's live kernel durations
   bool timing = false;
   std::vector<std::pair<int, cudaEvent_t>> marks;  // (phase that ENDS at this event, event)

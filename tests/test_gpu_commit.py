@@ -68,6 +68,34 @@ def test_commit_device_input_and_recommit(gpu_ctx):
     cm.free()
 
 
+@pytest.mark.parametrize("R,k", [(2200, 4096), (9000, 1024)])
+def test_host_input_pipeline_equals_device_input(gpu_ctx, R, k):
+    """Host matrices >= 64 MiB are uploaded in row tiles overlapped with the encoding (two tiles here); the
+    result must equal the device-resident path (itself checked against the oracle above) and the C oracle."""
+    import torch
+    from oracle import cref
+    rng = np.random.default_rng(R + k)
+    a = rng.integers(0, 2 ** 62, size=(R * k, 4), dtype=np.uint64)
+    a[:, 3] &= (1 << 60) - 1
+    a.reshape(R, k, 4)[R // 3] = 0                      # an all-zero row inside a tile
+    dev = torch.from_numpy(a.view(np.int64)).cuda()
+    cm_dev = gpu_ctx.commit(dev, R, k, 8)
+    cm_host = gpu_ctx.commit(a, R, k, 8)
+    try:
+        assert cm_host.root == cm_dev.root
+        assert np.array_equal(cm_host.read_rows(R - 2, 2), cm_dev.read_rows(R - 2, 2))
+        assert np.array_equal(cm_host.read_leaves(), cm_dev.read_leaves())
+        pinned = torch.from_numpy(a.view(np.int64)).pin_memory()
+        assert cm_host.recommit(pinned) == cm_dev.root
+        if k == 4096:
+            sub = 64                                    # C oracle on a row prefix: codeword rows must agree
+            ref = cref.commit(a[: sub * k], sub, k, 8, want_u=True)
+            assert np.array_equal(cm_host.read_rows(0, 2), ref["u"][:2])
+    finally:
+        cm_dev.free()
+        cm_host.free()
+
+
 def test_format_switches(gpu_ctx):
     rnd = random.Random(9)
     R, k, rho = 5, 8, 8
