@@ -63,6 +63,10 @@ void* lg_ctx_stream(const lg_ctx* ctx);
 #define LG_PHASE_OPEN 7            /* column gather */
 #define LG_PHASE_COUNT 8
 int lg_ctx_set_timing(lg_ctx* ctx, int enabled);
+/* lg_commit / lg_recommit of a large matrix run as a row-tile pipeline in which the column hashing of one
+ * tile overlaps the encoding of the next on a second stream (default).  enabled = 0 serialises the kernels
+ * (same results; used to time each kernel on its own). */
+int lg_ctx_set_overlap(lg_ctx* ctx, int enabled);
 int lg_ctx_phase_ms(lg_ctx* ctx, double* ms_out, uint64_t* count_out, int n);
 
 /* ---- encode + commit: replaces src/ligero/mod.rs:521-551 ------------------------------------ */
@@ -234,6 +238,9 @@ int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out);
 /* Runs dependent-chain microbenchmarks at full occupancy for ~`ms_target` milliseconds each and
  * reports sustained Montgomery multiplications/s and IMAD.WIDE.U32 (32x32+64) operations/s. */
 int lg_bench_int_peak(lg_ctx* ctx, double ms_target, double* fr_mul_per_s, double* imad_wide_per_s);
+/* measured by the same lg_bench_int_peak call: the encoder's own multiplier (table-constant products with a
+ * precomputed quotient, fr_lazy.cuh) and whole lazily reduced butterflies, per second per GPU */
+int lg_bench_shoup_peak(lg_ctx* ctx, double* shoup_mul_per_s, double* butterfly_per_s);
 
 #ifdef __cplusplus
 }

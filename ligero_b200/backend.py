@@ -96,6 +96,10 @@ class Context:
     def set_timing(self, enabled: bool = True):
         check(self.lib.lg_ctx_set_timing(self.handle, int(enabled)), self.handle)
 
+    def set_overlap(self, enabled: bool = True):
+        """Overlap column hashing with encoding inside commit/recommit (default on)."""
+        check(self.lib.lg_ctx_set_overlap(self.handle, int(enabled)), self.handle)
+
     def phase_ms(self):
         """{phase: (accumulated ms, intervals)} since the last call (synchronises the stream)."""
         n = len(self.PHASES)
@@ -158,7 +162,10 @@ class Context:
     def int_peak(self, ms_target: float = 50.0):
         a, b = c_double(), c_double()
         check(self.lib.lg_bench_int_peak(self.handle, ms_target, byref(a), byref(b)), self.handle, "lg_bench_int_peak")
-        return {"fr_mul_per_s": a.value, "imad_wide_per_s": b.value}
+        c, d = c_double(), c_double()
+        check(self.lib.lg_bench_shoup_peak(self.handle, byref(c), byref(d)), self.handle, "lg_bench_shoup_peak")
+        return {"fr_mul_per_s": a.value, "imad_wide_per_s": b.value, "shoup_mul_per_s": c.value,
+                "butterfly_per_s": d.value}
 
 
 class Constraints:

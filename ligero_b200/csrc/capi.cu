@@ -1,6 +1,7 @@
 // C ABI (include/ligero_b200.h) over the kernels: context, commit, read-backs, microbenchmarks.
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/ligero_b200.h"
@@ -64,9 +65,14 @@ __global__ void gather_rows_kernel(const Fr* __restrict__ u, size_t rows, int lo
     const size_t i = f / n, j = f % n;
     const size_t s = j % rho, c = j / rho;
     const uint4* src = reinterpret_cast<const uint4*>(u + s * rows * k + (row0 + i) * k + c);
+    const uint4 a = src[0], b = src[1];
+    Fr x;
+    x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
+    x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
+    if (s) x = fr_mul(x, fr_r2());  // coset planes hold plain integers (Matrix): back to Montgomery form
     uint4* dst = reinterpret_cast<uint4*>(out + f);
-    dst[0] = src[0];
-    dst[1] = src[1];
+    dst[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    dst[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
   }
 }
 
@@ -82,6 +88,33 @@ __global__ void __launch_bounds__(256) bench_fr_mul_kernel(Fr* io, int iters) {
     d = fr_mul(d, a);
   }
   io[t] = fr_add(fr_add(a, b), fr_add(c, d));
+}
+
+// the encoder's multiplier: table-constant products (fr_lazy.cuh), 4 independent chains per thread;
+// BFLY: whole forward butterflies (conditional subtraction, product, add, subtract) instead of bare products
+template <bool BFLY>
+__global__ void __launch_bounds__(256) bench_fr_shoup_kernel(Fr* io, int iters) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fr a = io[t], b = io[t + (size_t)gridDim.x * blockDim.x];
+  FrTw tw;
+  tw.w = fr_from_mont(a);
+  tw.w.v[7] &= 0x0fffffffu;  // < r
+  tw.p = fr_shoup_quotient(tw.w);
+  Fr c = fr_add(a, b), d = fr_sub(a, b);
+  for (int i = 0; i < iters; i++) {
+    if (BFLY) {
+      lz_bfly_dit(a, b, tw);
+      lz_bfly_dit(c, d, tw);
+      lz_bfly_dit(b, a, tw);
+      lz_bfly_dit(d, c, tw);
+    } else {
+      a = fr_mul_shoup(a, tw);
+      b = fr_mul_shoup(b, tw);
+      c = fr_mul_shoup(c, tw);
+      d = fr_mul_shoup(d, tw);
+    }
+  }
+  io[t] = fr_add(fr_add(fr_normalize(a), fr_normalize(b)), fr_add(fr_normalize(c), fr_normalize(d)));
 }
 
 __global__ void __launch_bounds__(256) bench_imad_wide_kernel(uint64_t* io, int iters) {
@@ -165,25 +198,45 @@ static int stage_input(lg_ctx* ctx, const uint64_t* src, size_t elems, const Fr*
   return OK;
 }
 
-// Host input: upload row tiles on a copy stream while the previous tile is being encoded.  Every tile is
-// encoded with an OutMap that drops its rows at their final position in the plane layout, so no tile ever
-// needs a second pass.  (Pinned host memory makes the copies truly asynchronous; pageable memory still works.)
-static int encode_host_pipelined(lg_matrix* h, const uint64_t* host) {
+// Row-tile pipeline of the commit.
+//  * host input: tile i+1 is uploaded on a copy stream while tile i is being encoded (pinned host memory makes
+//    the copies truly asynchronous; pageable memory still works);
+//  * `hash`: the BLAKE2s column hashing of tile i runs on a second, high-priority stream while tile i+1 is being
+//    encoded.  The encoder is bound by the integer-multiply pipe and the hash by the ALU pipe, so the two kernels
+//    share an SM instead of queueing; the per-column hash state travels between tiles in ctx->hash_state.
+// Every tile is encoded with an OutMap that drops its rows at their final position in the plane layout, so no
+// tile ever needs a second pass.
+static int encode_tiled(lg_matrix* h, const uint64_t* src, bool host, bool hash) {
   Matrix& m = h->m;
   Ctx* c = m.ctx;
   const size_t row_bytes = m.k * sizeof(Fr);
-  size_t tile_rows = ((size_t)256 << 20) / row_bytes;
-  if (tile_rows < 1) tile_rows = 1;
+  size_t tile_rows = (((size_t)256 << 20) / row_bytes) & ~(size_t)1;
+  if (tile_rows < 2) tile_rows = 2;
   if (tile_rows > m.rows) tile_rows = m.rows;
   const size_t tile_bytes = tile_rows * row_bytes;
-  if (!c->copy_stream) {
+  if (host && !c->copy_stream) {
     LG_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
       LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
       LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
   }
-  if (c->stage_bytes < tile_bytes) {
+  if (hash && !c->hash_stream) {
+    int lo = 0, hi = 0;
+    LG_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LG_CUDA(c, cudaStreamCreateWithPriority(&c->hash_stream, cudaStreamNonBlocking, lo));
+    LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_encoded, cudaEventDisableTiming));
+    LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_hashed, cudaEventDisableTiming));
+  }
+  if (hash && c->hash_state_words < 10 * m.n) {
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->hash_stream));
+    if (c->hash_state) cudaFree(c->hash_state);
+    c->hash_state = nullptr;
+    LG_CUDA(c, cudaMalloc(&c->hash_state, 10 * m.n * sizeof(uint32_t)));
+    c->hash_state_words = 10 * m.n;
+  }
+  if (host && c->stage_bytes < tile_bytes) {
     LG_CUDA(c, cudaStreamSynchronize(c->stream));
     LG_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     for (int i = 0; i < 2; i++) {
@@ -205,36 +258,56 @@ static int encode_host_pipelined(lg_matrix* h, const uint64_t* host) {
   map.base[0] = m.u;
   map.log_kg = m.log_k;
   map.rows_total = m.rows;
-  // the copy stream must not overwrite a staging tile that an earlier call is still reading
-  LG_CUDA(c, cudaEventRecord(c->ev_consumed[0], c->stream));
-  LG_CUDA(c, cudaEventRecord(c->ev_consumed[1], c->stream));
+  if (host) {
+    // the copy stream must not overwrite a staging tile that an earlier call is still reading
+    LG_CUDA(c, cudaEventRecord(c->ev_consumed[0], c->stream));
+    LG_CUDA(c, cudaEventRecord(c->ev_consumed[1], c->stream));
+  }
   int t = 0;
   for (size_t row0 = 0; row0 < m.rows; row0 += tile_rows, t++) {
     const size_t nr = row0 + tile_rows <= m.rows ? tile_rows : m.rows - row0;
+    const Fr* tile = reinterpret_cast<const Fr*>(src) + row0 * m.k;
     const int b = t & 1;
-    LG_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
-    LG_CUDA(c, cudaMemcpyAsync(c->stage[b], (const uint8_t*)host + row0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice,
-                               c->copy_stream));
-    LG_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
-    LG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    if (host) {
+      LG_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+      LG_CUDA(c, cudaMemcpyAsync(c->stage[b], (const uint8_t*)src + row0 * row_bytes, nr * row_bytes,
+                                 cudaMemcpyHostToDevice, c->copy_stream));
+      LG_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+      LG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+      tile = (const Fr*)c->stage[b];
+    }
     map.m = map.m_g = (uint32_t)nr;  // one block: grow(i) = row0 + i
     map.i0 = (uint32_t)row0;
-    LG_TRY(encode_rows(c, (const Fr*)c->stage[b], nr, m.log_k, m.rho_inv, nullptr, (Fr*)c->tile_cosets, &map));
-    LG_CUDA(c, cudaEventRecord(c->ev_consumed[b], c->stream));
+    LG_TRY(encode_rows(c, tile, nr, m.log_k, m.rho_inv, nullptr, (Fr*)c->tile_cosets, &map, true));
+    if (host) LG_CUDA(c, cudaEventRecord(c->ev_consumed[b], c->stream));
+    if (hash) {
+      LG_CUDA(c, cudaEventRecord(c->ev_encoded, c->stream));
+      LG_CUDA(c, cudaStreamWaitEvent(c->hash_stream, c->ev_encoded, 0));
+      LG_TRY(hash_columns_range(c, c->hash_stream, m.u, m.rows, m.log_k, m.rho_inv, row0, row0 + nr, c->hash_state,
+                                m.leaves, h->owner->col_len_prefix));
+    }
+  }
+  if (hash) {
+    LG_TRY(merkle_build(c, m.leaves, m.n, m.nodes, h->owner->leaf_len_prefix, c->hash_stream));
+    LG_CUDA(c, cudaEventRecord(c->ev_hashed, c->hash_stream));
+    LG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_hashed, 0));
   }
   return OK;
+}
+
+static bool tiled_shape(const Matrix& m) {
+  return m.rows * m.k * sizeof(Fr) >= ((size_t)64 << 20) && m.rows < ((size_t)1 << 31);
 }
 
 static int do_encode(lg_matrix* h, const uint64_t* preenc_u) {
   Matrix& m = h->m;
   Ctx* c = m.ctx;
   if (!preenc_u) return set_error(c, ERR_INVALID, "null input matrix");
-  if (!is_device_ptr(preenc_u) && m.rows * m.k * sizeof(Fr) >= ((size_t)64 << 20) && m.rows < ((size_t)1 << 31))
-    return encode_host_pipelined(h, preenc_u);
+  if (!is_device_ptr(preenc_u) && tiled_shape(m)) return encode_tiled(h, preenc_u, true, false);
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(h->owner, preenc_u, m.rows * m.k, &dev, &to_free));
-  int s = encode_rows(c, dev, m.rows, m.log_k, m.rho_inv, m.u, m.u + m.rows * m.k);
+  int s = encode_rows(c, dev, m.rows, m.log_k, m.rho_inv, m.u, m.u + m.rows * m.k, nullptr, true);
   if (to_free) {
     cudaStreamSynchronize(c->stream);
     cudaFree(to_free);
@@ -257,6 +330,27 @@ static int do_hash(lg_matrix* h, uint8_t root_out[32]) {
   return OK;
 }
 
+// encode + hash + Merkle tree.  Large matrices go through the row-tile pipeline with the hashing overlapped
+// (ctx->overlap, on by default; lg_ctx_set_overlap(ctx, 0) serialises the kernels, e.g. to time them one by one)
+static int do_commit(lg_matrix* h, const uint64_t* preenc_u, uint8_t root_out[32]) {
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  if (!preenc_u) return set_error(c, ERR_INVALID, "null input matrix");
+  // host input goes through the row-tile pipeline anyway (upload overlapped with encoding); hashing tile by tile
+  // there finishes most of the column hashes before the last tile is encoded.  With the matrix already in HBM the
+  // plain sequence is faster: both kernels saturate the SM's issue port, so sharing an SM gains nothing (measured)
+  if (c->overlap && tiled_shape(m) && !is_device_ptr(preenc_u)) {
+    LG_TRY(encode_tiled(h, preenc_u, true, true));
+    if (root_out) {
+      LG_CUDA(c, cudaMemcpyAsync(root_out, m.nodes, 32, cudaMemcpyDeviceToHost, c->stream));
+      LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return OK;
+  }
+  LG_TRY(do_encode(h, preenc_u));
+  return do_hash(h, root_out);
+}
+
 }  // namespace lg
 
 using namespace lg;
@@ -277,11 +371,16 @@ int lg_ctx_create(int device, lg_ctx** out) {
   lg_ctx* ctx = new (std::nothrow) lg_ctx();
   if (!ctx) return ERR_NOMEM;
   ctx->c.device = device;
-  if (cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // the main stream gets the greatest priority: the overlapped column hashing (lowest priority, its own stream)
+  // then only fills the registers and issue slots the encoder leaves free
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&ctx->c.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete ctx;
     return ERR_CUDA;
   }
   cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (const char* e = getenv("LG_OVERLAP")) ctx->c.overlap = atoi(e) != 0;  // tuning hook; see lg_ctx_set_overlap
   *out = ctx;
   return OK;
 }
@@ -291,9 +390,7 @@ int lg_ctx_destroy(lg_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   for (auto& kv : ctx->c.tables) {
-    cudaFree(kv.second.w_fwd);
-    cudaFree(kv.second.w_inv);
-    cudaFree(kv.second.scale);
+    cudaFree(kv.second.w_fwd);  // w_inv and scale live in the same allocation
   }
   if (ctx->c.scratch) cudaFree(ctx->c.scratch);
   if (ctx->c.copy_stream) {
@@ -303,9 +400,16 @@ int lg_ctx_destroy(lg_ctx* ctx) {
       if (ctx->c.ev_copied[i]) cudaEventDestroy(ctx->c.ev_copied[i]);
       if (ctx->c.ev_consumed[i]) cudaEventDestroy(ctx->c.ev_consumed[i]);
     }
-    if (ctx->c.tile_cosets) cudaFree(ctx->c.tile_cosets);
     cudaStreamDestroy(ctx->c.copy_stream);
   }
+  if (ctx->c.hash_stream) {
+    cudaStreamSynchronize(ctx->c.hash_stream);
+    cudaStreamDestroy(ctx->c.hash_stream);
+    cudaEventDestroy(ctx->c.ev_encoded);
+    cudaEventDestroy(ctx->c.ev_hashed);
+    if (ctx->c.hash_state) cudaFree(ctx->c.hash_state);
+  }
+  if (ctx->c.tile_cosets) cudaFree(ctx->c.tile_cosets);
   for (auto& m : ctx->c.marks) cudaEventDestroy(m.second);
   for (auto& e : ctx->c.event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->c.stream);
@@ -331,6 +435,12 @@ int lg_ctx_set_formats(lg_ctx* ctx, int col_len_prefix, int leaf_len_prefix) {
 }
 
 void* lg_ctx_stream(const lg_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nullptr; }
+
+int lg_ctx_set_overlap(lg_ctx* ctx, int enabled) {
+  if (!ctx) return ERR_INVALID;
+  ctx->c.overlap = enabled != 0;
+  return OK;
+}
 
 int lg_ctx_set_timing(lg_ctx* ctx, int enabled) {
   if (!ctx) return ERR_INVALID;
@@ -397,8 +507,9 @@ int lg_commit(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint
               lg_matrix** out) {
   if (!ctx) return ERR_INVALID;
   lg_matrix* h = nullptr;
-  LG_TRY(lg_encode(ctx, preenc_u, rows, k, rho_inv, &h));
-  int s = do_hash(h, root_out);
+  cudaSetDevice(ctx->c.device);
+  LG_TRY(matrix_alloc(ctx, rows, k, rho_inv, &h));
+  int s = do_commit(h, preenc_u, root_out);
   if (s != OK) {
     lg_matrix_free(h);
     return s;
@@ -410,8 +521,7 @@ int lg_commit(lg_ctx* ctx, const uint64_t* preenc_u, size_t rows, size_t k, uint
 int lg_recommit(lg_matrix* m, const uint64_t* preenc_u, uint8_t root_out[32]) {
   if (!m) return ERR_INVALID;
   cudaSetDevice(m->m.ctx->device);
-  LG_TRY(do_encode(m, preenc_u));
-  return do_hash(m, root_out);
+  return do_commit(m, preenc_u, root_out);
 }
 
 int lg_matrix_free(lg_matrix* m) {
@@ -497,7 +607,7 @@ int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(ctx, msg_local, rows * k, &dev, &to_free));
-  int s = encode_rows(c, dev, rows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map);
+  int s = encode_rows(c, dev, rows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map, true);
   if (to_free) {
     cudaStreamSynchronize(c->stream);
     cudaFree(to_free);
@@ -575,6 +685,13 @@ int lg_intt(lg_ctx* ctx, const uint64_t* in, uint64_t* out, size_t rows, size_t 
   return s;
 }
 
+int lg_bench_shoup_peak(lg_ctx* ctx, double* shoup_mul_per_s, double* butterfly_per_s) {
+  if (!ctx) return ERR_INVALID;
+  if (shoup_mul_per_s) *shoup_mul_per_s = ctx->c.last_shoup_peak[0];
+  if (butterfly_per_s) *butterfly_per_s = ctx->c.last_shoup_peak[1];
+  return OK;
+}
+
 int lg_bench_int_peak(lg_ctx* ctx, double ms_target, double* fr_mul_per_s, double* imad_wide_per_s) {
   if (!ctx) return ERR_INVALID;
   Ctx* c = &ctx->c;
@@ -600,6 +717,21 @@ int lg_bench_int_peak(lg_ctx* ctx, double ms_target, double* fr_mul_per_s, doubl
     if (rep == 0 && ms > 0) iters = (int)(iters * ms_target / ms) + 1;
   }
   if (fr_mul_per_s) *fr_mul_per_s = 4.0 * iters * (double)nthreads / (ms * 1e-3);
+  // table-constant (Shoup) products and whole lazy butterflies: what the encoder actually executes
+  for (int which = 0; which < 2; which++) {
+    iters = 64;
+    for (int rep = 0; rep < 3; rep++) {
+      cudaEventRecord(e0, c->stream);
+      if (which) bench_fr_shoup_kernel<true><<<blocks, threads, 0, c->stream>>>(buf, iters);
+      else bench_fr_shoup_kernel<false><<<blocks, threads, 0, c->stream>>>(buf, iters);
+      cudaEventRecord(e1, c->stream);
+      cudaEventSynchronize(e1);
+      cudaEventElapsedTime(&ms, e0, e1);
+      c->launches++;
+      if (rep == 0 && ms > 0) iters = (int)(iters * ms_target / ms) + 1;
+    }
+    c->last_shoup_peak[which] = 4.0 * iters * (double)nthreads / (ms * 1e-3);
+  }
   // raw IMAD.WIDE.U32
   iters = 64;
   for (int rep = 0; rep < 3; rep++) {

@@ -197,7 +197,8 @@ static int linear_test_core(lg_matrix* h, Fr* r_a, uint64_t* coeffs_out, size_t*
   phase_mark(c, PH_BEGIN);
   // q(zeta^(2c)) = sum_i r_a[i][c] U[i][rho c];   q(zeta^(2c+1)) = sum_i r_odd[i][c] U[i][rho c + rho/2]
   LG_TRY(col_reduce(c, 1, r_a, m.u, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 0));
-  LG_TRY(col_reduce(c, 1, (const Fr*)odd.p, m.u + (size_t)(m.rho_inv / 2) * plane, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 1));
+  LG_TRY(col_reduce(c, 1, (const Fr*)odd.p, m.u + (size_t)(m.rho_inv / 2) * plane, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 1,
+                    true));  // coset planes of the committed matrix hold plain integers
   phase_mark(c, PH_TESTS);
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);
 }
@@ -245,7 +246,7 @@ int lg_quadratic_test(lg_matrix* h, const uint64_t* r_quad, uint64_t* coeffs_out
   phase_mark(c, PH_BEGIN);
   for (int half = 0; half < 2; half++) {
     const Fr* p = m.u + (size_t)(half ? m.rho_inv / 2 : 0) * plane;
-    LG_TRY(col_reduce(c, 2, (const Fr*)rin.ptr, p, p + mm * m.k, p + 2 * mm * m.k, mm, m.k, (Fr*)qhat.p, 2, half));
+    LG_TRY(col_reduce(c, 2, (const Fr*)rin.ptr, p, p + mm * m.k, p + 2 * mm * m.k, mm, m.k, (Fr*)qhat.p, 2, half, half != 0));
   }
   phase_mark(c, PH_TESTS);
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);

@@ -50,6 +50,13 @@ LG_HD Fr fr_one() {
   o.v[4] = 0x7879462eu; o.v[5] = 0x666ea36fu; o.v[6] = 0x9a07df2fu; o.v[7] = 0x0e0a77c1u;
   return o;
 }
+// R^2 mod r: multiplying by it takes a plain integer (< r) to its Montgomery form
+LG_HD Fr fr_r2() {
+  Fr o;
+  o.v[0] = 0xae216da7u; o.v[1] = 0x1bb8e645u; o.v[2] = 0xe35c59e3u; o.v[3] = 0x53fe3ab1u;
+  o.v[4] = 0x53bb8085u; o.v[5] = 0x8c49833du; o.v[6] = 0x7f4e44a5u; o.v[7] = 0x0216d0b1u;
+  return o;
+}
 LG_HD Fr fr_zero() {
   Fr o;
 #pragma unroll

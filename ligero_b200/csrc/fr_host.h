@@ -9,14 +9,6 @@
 
 namespace lg {
 
-// R^2 mod r (to_mont multiplier)
-inline Fr fr_r2() {
-  Fr o;
-  o.v[0] = 0xae216da7u; o.v[1] = 0x1bb8e645u; o.v[2] = 0xe35c59e3u; o.v[3] = 0x53fe3ab1u;
-  o.v[4] = 0x53bb8085u; o.v[5] = 0x8c49833du; o.v[6] = 0x7f4e44a5u; o.v[7] = 0x0216d0b1u;
-  return o;
-}
-
 // canonical integer (< r) in limbs -> Montgomery form
 inline Fr fr_to_mont(const Fr& canonical) { return fr_mul(canonical, fr_r2()); }
 

@@ -78,22 +78,25 @@ __device__ __forceinline__ void blake2s_init(uint32_t (&h)[8]) {
 
 // One thread per column.  `col` points at the column's first element; consecutive rows are `stride`
 // elements apart.  MONT: elements are in Montgomery form and are converted in registers.
+// The 64-byte blocks [b0, b1) of the column message are compressed; block b holds rows 2b and 2b+1
+// (shifted by the 8-byte length prefix, whose spill-over travels in c0/c1).  A column can therefore be
+// hashed in row tiles -- (h, c0, c1) is the whole carried state -- which lets the commit overlap the
+// hashing of one tile with the encoding of the next.  Rows at or beyond `row_lim` are not read.
 template <bool PREFIX, bool MONT>
-__device__ __forceinline__ void hash_one_column(const Fr* col, size_t stride, size_t rows, uint32_t (&h)[8]) {
-  blake2s_init(h);
+__device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride, size_t rows, size_t row_lim, uint64_t b0,
+                                                   uint64_t b1, uint32_t (&h)[8], uint32_t& c0, uint32_t& c1) {
   const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
   const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
-  uint32_t c0 = (uint32_t)rows, c1 = (uint32_t)((uint64_t)rows >> 32);  // carry words (PREFIX): u64_le(R) first
   Fr n0 = fr_zero(), n1 = fr_zero();
-  if (0 < rows) n0 = ld_fr_g(col);
-  if (1 < rows) n1 = ld_fr_g(col + stride);
-  for (uint64_t b = 0; b < nblocks; b++) {
+  if (2 * b0 < row_lim) n0 = ld_fr_g(col + 2 * b0 * stride);
+  if (2 * b0 + 1 < row_lim) n1 = ld_fr_g(col + (2 * b0 + 1) * stride);
+  for (uint64_t b = b0; b < b1; b++) {
     Fr e0 = n0, e1 = n1;
     const size_t r2 = 2 * (b + 1);
     n0 = fr_zero();
     n1 = fr_zero();
-    if (r2 < rows) n0 = ld_fr_g(col + r2 * stride);          // prefetch the next block's two elements
-    if (r2 + 1 < rows) n1 = ld_fr_g(col + (r2 + 1) * stride);
+    if (r2 < row_lim) n0 = ld_fr_g(col + r2 * stride);          // prefetch the next block's two elements
+    if (r2 + 1 < row_lim) n1 = ld_fr_g(col + (r2 + 1) * stride);
     if (MONT) {
       e0 = fr_from_mont(e0);
       e1 = fr_from_mont(e1);
@@ -116,15 +119,54 @@ __device__ __forceinline__ void hash_one_column(const Fr* col, size_t stride, si
   }
 }
 
+template <bool PREFIX, bool MONT>
+__device__ __forceinline__ void hash_one_column(const Fr* col, size_t stride, size_t rows, uint32_t (&h)[8]) {
+  blake2s_init(h);
+  const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
+  const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
+  uint32_t c0 = (uint32_t)rows, c1 = (uint32_t)((uint64_t)rows >> 32);  // carry words (PREFIX): u64_le(R) first
+  hash_column_blocks<PREFIX, MONT>(col, stride, rows, rows, 0, nblocks, h, c0, c1);
+}
+
+// rows [row0, row_end) of every column; row0 even, row_end even unless it is `rows`.  `state` carries
+// (h[8], c0, c1) per physical column between tiles, word-major so a warp's accesses coalesce.
 template <bool PREFIX>
 __global__ void __launch_bounds__(64) hash_columns_kernel(const Fr* __restrict__ u, size_t rows, int log_k, int rho,
+                                                          size_t row0, size_t row_end, uint32_t* __restrict__ state,
                                                           uint8_t* __restrict__ leaves) {
   const size_t pc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // physical column = plane * k + c
-  const size_t k = (size_t)1 << log_k;
-  if (pc >= (size_t)rho * k) return;
+  const size_t k = (size_t)1 << log_k, ncols = (size_t)rho * k;
+  if (pc >= ncols) return;
   const size_t s = pc >> log_k, c = pc & (k - 1);
-  uint32_t h[8];
-  hash_one_column<PREFIX, true>(u + s * rows * k + c, k, rows, h);
+  const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
+  const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
+  const bool first = row0 == 0, last = row_end >= rows;
+  uint32_t h[8], c0, c1;
+  if (first) {
+    blake2s_init(h);
+    c0 = (uint32_t)rows;
+    c1 = (uint32_t)((uint64_t)rows >> 32);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = state[(size_t)i * ncols + pc];
+    c0 = state[8 * ncols + pc];
+    c1 = state[9 * ncols + pc];
+  }
+  // plane 0 is the caller's Montgomery-form message (converted in registers); the coset planes already hold
+  // the plain integers (Matrix).  With k >= 32 columns per plane the branch is warp-uniform
+  if (s == 0)
+    hash_column_blocks<PREFIX, true>(u + c, k, rows, row_end < rows ? row_end : rows, row0 / 2,
+                                     last ? nblocks : row_end / 2, h, c0, c1);
+  else
+    hash_column_blocks<PREFIX, false>(u + s * rows * k + c, k, rows, row_end < rows ? row_end : rows, row0 / 2,
+                                      last ? nblocks : row_end / 2, h, c0, c1);
+  if (!last) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) state[(size_t)i * ncols + pc] = h[i];
+    state[8 * ncols + pc] = c0;
+    state[9 * ncols + pc] = c1;
+    return;
+  }
   uint4* dst = reinterpret_cast<uint4*>(leaves + 32 * ((size_t)rho * c + s));  // logical column rho*c + s
   dst[0] = make_uint4(h[0], h[1], h[2], h[3]);
   dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
@@ -143,15 +185,22 @@ __global__ void hash_column_list_kernel(const Fr* __restrict__ cols, size_t rows
   dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
-int hash_columns(Ctx* ctx, const Fr* u, size_t rows, int log_k, int rho_inv, uint8_t* leaves, bool len_prefix) {
+int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u, size_t rows, int log_k, int rho_inv, size_t row0,
+                       size_t row_end, uint32_t* state, uint8_t* leaves, bool len_prefix) {
+  if ((row0 & 1) || (row_end < rows && (row_end & 1)) || ((row0 > 0 || row_end < rows) && !state))
+    return set_error(ctx, ERR_INVALID, "column hashing tiles must start and end on even rows and carry a state buffer");
   const size_t n = (size_t)rho_inv << log_k;
   const unsigned bs = 64;
   const unsigned grid = (unsigned)((n + bs - 1) / bs);
-  if (len_prefix) hash_columns_kernel<true><<<grid, bs, 0, ctx->stream>>>(u, rows, log_k, rho_inv, leaves);
-  else hash_columns_kernel<false><<<grid, bs, 0, ctx->stream>>>(u, rows, log_k, rho_inv, leaves);
+  if (len_prefix) hash_columns_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+  else hash_columns_kernel<false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
+}
+
+int hash_columns(Ctx* ctx, const Fr* u, size_t rows, int log_k, int rho_inv, uint8_t* leaves, bool len_prefix) {
+  return hash_columns_range(ctx, ctx->stream, u, rows, log_k, rho_inv, 0, rows, nullptr, leaves, len_prefix);
 }
 
 int hash_column_list(Ctx* ctx, const Fr* cols, size_t rows, size_t count, uint8_t* digests, bool len_prefix) {
@@ -283,20 +332,21 @@ __global__ void merkle_top_kernel(uint8_t* nodes, size_t width) {
   }
 }
 
-int merkle_build(Ctx* ctx, const uint8_t* leaves, size_t n, uint8_t* nodes, bool leaf_len_prefix) {
+int merkle_build(Ctx* ctx, const uint8_t* leaves, size_t n, uint8_t* nodes, bool leaf_len_prefix, cudaStream_t st) {
+  if (!st) st = ctx->stream;
   if (n < 2 || (n & (n - 1))) return set_error(ctx, ERR_INVALID, "merkle tree needs a power-of-two number (>1) of leaves");
   const size_t half = n / 2;
   const unsigned bs = 128;
-  if (leaf_len_prefix) merkle_bottom_kernel<true><<<(unsigned)((half + bs - 1) / bs), bs, 0, ctx->stream>>>(leaves, nodes, half);
-  else merkle_bottom_kernel<false><<<(unsigned)((half + bs - 1) / bs), bs, 0, ctx->stream>>>(leaves, nodes, half);
+  if (leaf_len_prefix) merkle_bottom_kernel<true><<<(unsigned)((half + bs - 1) / bs), bs, 0, st>>>(leaves, nodes, half);
+  else merkle_bottom_kernel<false><<<(unsigned)((half + bs - 1) / bs), bs, 0, st>>>(leaves, nodes, half);
   ctx->launches++;
   size_t w = half / 2;
   for (; w > 256; w >>= 1) {
-    merkle_level_kernel<<<(unsigned)((w + bs - 1) / bs), bs, 0, ctx->stream>>>(nodes, w);
+    merkle_level_kernel<<<(unsigned)((w + bs - 1) / bs), bs, 0, st>>>(nodes, w);
     ctx->launches++;
   }
   if (w >= 1) {
-    merkle_top_kernel<<<1, 256, 0, ctx->stream>>>(nodes, w);
+    merkle_top_kernel<<<1, 256, 0, st>>>(nodes, w);
     ctx->launches++;
   }
   LG_CUDA(ctx, cudaGetLastError());

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "fr.cuh"
+#include "fr_lazy.cuh"
 
 namespace lg {
 
@@ -40,9 +41,11 @@ int set_error(Ctx* ctx, int code, const std::string& msg);
 struct NttTables {
   int log_k = 0;
   int rho_inv = 0;
-  Fr* w_fwd = nullptr;   // omega_k^i,  i < max(1, k/2)
-  Fr* w_inv = nullptr;   // omega_k^-i
-  Fr* scale = nullptr;   // (rho_inv-1) tables of k: scale[(s-1)*k + pos] = g^(s*bitrev(pos)) / k,  g = omega_{rho_inv*k}
+  // {plain integer, quotient multiplier} entries (fr_lazy.cuh); one allocation, w_fwd is its base
+  FrTw* w_fwd = nullptr;   // omega_k^i,  i < max(1, k/2)
+  FrTw* w_inv = nullptr;   // omega_k^-i
+  FrTw* scale = nullptr;   // (rho_inv-1) tables of k: scale[(s-1)*k + pos] = g^(s*bitrev(pos)) / k,  g = omega_{rho_inv*k}
+  FrTw kinv;               // 1/k
 };
 
 struct Ctx {
@@ -50,7 +53,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   std::string last_error;
-  std::map<std::pair<int, int>, NttTables> tables;  // (log_k, rho_inv)
+  std::map<std::pair<int, int>, NttTables> tables;  // (log_k, rho_inv | plain << 16)
   // kernel launch counter (bench.py's "gpu_launches")
   uint64_t launches = 0;
   // scratch reused across calls
@@ -64,6 +67,13 @@ struct Ctx {
   size_t stage_bytes = 0;
   void* tile_cosets = nullptr;
   size_t tile_cosets_bytes = 0;
+  // commit pipeline: column hashing of row tile i (high-priority stream) overlaps the encoding of tile i+1
+  double last_shoup_peak[2] = {0, 0};  // lg_bench_int_peak: table-constant products/s, lazy butterflies/s
+  bool overlap = true;
+  cudaStream_t hash_stream = nullptr;
+  cudaEvent_t ev_encoded = nullptr, ev_hashed = nullptr;
+  uint32_t* hash_state = nullptr;
+  size_t hash_state_words = 0;
   // optional per-phase device timing (CUDA events on `stream`): bench.py's live kernel durations
   bool timing = false;
   std::vector<std::pair<int, cudaEvent_t>> marks;  // (phase that ENDS at this event, event)
@@ -76,12 +86,17 @@ enum Phase : int { PH_BEGIN = -1, PH_NTT_STRIDED_INV = 0, PH_NTT_LOCAL = 1, PH_N
 void phase_mark(Ctx* ctx, int phase_ended);
 
 int ctx_scratch(Ctx* ctx, size_t bytes, void** out);
-int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out);
+// plain: the coset scale factors carry an extra R^-1, so the coset planes come out as plain integers
+int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool plain = false);
 
 // ---- committed matrix ------------------------------------------------------------------------------
 // Physical layout of U (R x n, n = rho_inv*k) in HBM: rho_inv "coset planes", each R x k row-major:
 //     plane[s][i][c] = U[i][rho_inv*c + s] = p_i(g^s * omega_k^c)
-// plane 0 is the message itself (systematic positions, src/ligero/mod.rs:89).
+// plane 0 is the message itself (systematic positions, src/ligero/mod.rs:89), in the caller's Montgomery form.
+// Planes s >= 1 hold the PLAIN integers (a, not a*R): the column hash needs exactly those bytes, and the
+// encoder produces them for free by folding R^-1 into the coset scale table (the transform is linear), which
+// removes one Montgomery reduction per codeword element from the hash kernel.  Everything that reads U back
+// (openings, row read-back, the two test reductions on plane rho_inv/2) converts on the fly.
 struct Matrix {
   Ctx* ctx = nullptr;
   size_t rows = 0;      // R
@@ -122,12 +137,14 @@ __device__ __forceinline__ Fr* outmap_ptr(const OutMap& o, uint32_t s, uint32_t 
 // plane0 (nullable) receives a copy of the message; cosets receives the rho_inv-1 planes s = 1..rho_inv-1
 // map (nullable): final destination of every element (multi-GPU); `cosets` is then only the local
 // intermediate of rows longer than one CTA tile and plane0 is ignored
+// plain_cosets: coset planes as plain integers (the committed matrix, see Matrix) instead of Montgomery form
 int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets,
-                const OutMap* map = nullptr);
+                const OutMap* map = nullptr, bool plain_cosets = false);
 // protocol.cu
 int expand_fr(Ctx* ctx, const uint8_t seed[32], size_t count, Fr* out_dev);
+// x_plain: X (and Y, Z) hold plain integers (a coset plane s >= 1 of a committed matrix); the result is Montgomery
 int col_reduce(Ctx* ctx, int mode, const Fr* W, const Fr* X, const Fr* Y, const Fr* Z, size_t rows, size_t k, Fr* out,
-               size_t out_stride, size_t out_offset);
+               size_t out_stride, size_t out_offset, bool x_plain = false);
 int spmv_right_block(Ctx* ctx, const uint32_t* col_ptr, const uint32_t* row_idx, const uint32_t* val_id, const Fr* consts,
                      const Fr* r, size_t mk, Fr* out);
 struct Matrix;
@@ -138,7 +155,12 @@ int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k);
 int hash_columns(Ctx* ctx, const Fr* u_planes, size_t rows, int log_k, int rho_inv, uint8_t* leaves,
                  bool len_prefix);
 // Merkle tree (a6)
-int merkle_build(Ctx* ctx, const uint8_t* leaves, size_t n, uint8_t* nodes, bool leaf_len_prefix);
+int merkle_build(Ctx* ctx, const uint8_t* leaves, size_t n, uint8_t* nodes, bool leaf_len_prefix,
+                 cudaStream_t st = nullptr);
+// the same column hash over the row tile [row0, row_end) only (even boundaries), carrying the BLAKE2s state
+// of every column in `state` (10 x n words) between tiles; the tile that ends at `rows` writes the leaves
+int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u_planes, size_t rows, int log_k, int rho_inv, size_t row0,
+                       size_t row_end, uint32_t* state, uint8_t* leaves, bool len_prefix);
 // BLAKE2s of `count` explicit columns (each `rows` contiguous Montgomery elements)
 int hash_column_list(Ctx* ctx, const Fr* cols, size_t rows, size_t count, uint8_t* digests, bool len_prefix);
 

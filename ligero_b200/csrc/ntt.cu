@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "fr_host.h"
+#include "fr_lazy.cuh"
 #include "lg_internal.h"
 
 namespace lg {
@@ -30,6 +31,13 @@ __device__ __forceinline__ Fr fr_pack(const uint4& a, const uint4& b) {
 __device__ __forceinline__ Fr ldg_fr(const Fr* p) {  // read-only path (tables)
   const uint4* q = reinterpret_cast<const uint4*>(p);
   return fr_pack(__ldg(q), __ldg(q + 1));
+}
+__device__ __forceinline__ FrTw ldg_tw(const FrTw* p) {  // table entry: constant + quotient multiplier
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  FrTw t;
+  t.w = fr_pack(__ldg(q), __ldg(q + 1));
+  t.p = fr_pack(__ldg(q + 2), __ldg(q + 3));
+  return t;
 }
 __device__ __forceinline__ Fr ld_fr(const Fr* p) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
@@ -62,10 +70,12 @@ __device__ __forceinline__ void sts_fr(uint4* lo, uint4* hi, uint32_t i, const F
 //   DIT (forward): v = x1 * w^j ; (x0, x1) = (x0 + v, x0 - v)          stages ascending
 //   DIF (inverse): (x0, x1) = (x0 + x1, (x0 - x1) * w^-j)              stages descending
 // with j = index mod 2^stage and twiddle W[j << (q - stage - 1)], W the order-2^q table.
+// Values stay lazily reduced between stages (fr_lazy.cuh): < 4r + d forward, < 2r + d inverse; whoever
+// stores a FINISHED element applies fr_normalize, so what reaches U is the canonical representative.
 // ------------------------------------------------------------------------------------------------
 template <int R, bool DIF>
 __device__ __forceinline__ void butterflies(Fr (&x)[1 << R], uint32_t t_lo, int s, int q,
-                                            const Fr* __restrict__ W) {
+                                            const FrTw* __restrict__ W) {
 #pragma unroll
   for (int bb = 0; bb < R; bb++) {
     const int b = DIF ? (R - 1 - bb) : bb;
@@ -77,25 +87,16 @@ __device__ __forceinline__ void butterflies(Fr (&x)[1 << R], uint32_t t_lo, int 
 #pragma unroll
         for (int eh = 0; eh < (1 << (R - 1 - b)); eh++) {
           const int e0 = el | (eh << (b + 1)), e1 = e0 | (1 << b);
-          const Fr u = x[e0], v = x[e1];
-          x[e0] = fr_add(u, v);
-          x[e1] = fr_sub(u, v);
+          if (!DIF) lz_bfly_dit1(x[e0], x[e1]);
+          else lz_bfly_dif1(x[e0], x[e1]);
         }
       } else {
-        const Fr w = ldg_fr(W + ((size_t)j << shift));
+        const FrTw w = ldg_tw(W + ((size_t)j << shift));
 #pragma unroll
         for (int eh = 0; eh < (1 << (R - 1 - b)); eh++) {
           const int e0 = el | (eh << (b + 1)), e1 = e0 | (1 << b);
-          if (!DIF) {
-            const Fr u = x[e0];
-            const Fr v = fr_mul(x[e1], w);
-            x[e0] = fr_add(u, v);
-            x[e1] = fr_sub(u, v);
-          } else {
-            const Fr u = x[e0], v = x[e1];
-            x[e0] = fr_add(u, v);
-            x[e1] = fr_mul(fr_sub(u, v), w);
-          }
+          if (!DIF) lz_bfly_dit(x[e0], x[e1], w);
+          else lz_bfly_dif(x[e0], x[e1], w);
         }
       }
     }
@@ -105,8 +106,9 @@ __device__ __forceinline__ void butterflies(Fr (&x)[1 << R], uint32_t t_lo, int 
 // one radix-2^R pass over E elements held in shared memory (src planes -> dst planes; may alias)
 template <int R, bool DIF, bool SCALE>
 __device__ __forceinline__ void smem_pass(const uint4* slo, const uint4* shi, uint4* dlo, uint4* dhi, int s, int q,
-                                          const Fr* __restrict__ W, const Fr* __restrict__ scale, uint32_t col_base,
+                                          const FrTw* __restrict__ W, const FrTw* __restrict__ scale, uint32_t col_base,
                                           uint32_t col_mask, int E, int NT) {
+#pragma unroll 2
   for (int g = threadIdx.x; g < (E >> R); g += NT) {
     const uint32_t t_lo = g & ((1u << s) - 1u), t_hi = (uint32_t)g >> s;
     const uint32_t base = (t_hi << (s + R)) | t_lo;
@@ -115,7 +117,7 @@ __device__ __forceinline__ void smem_pass(const uint4* slo, const uint4* shi, ui
     for (int e = 0; e < (1 << R); e++) {
       const uint32_t idx = base | ((uint32_t)e << s);
       x[e] = lds_fr(slo, shi, idx);
-      if (SCALE) x[e] = fr_mul(x[e], ldg_fr(scale + ((col_base + idx) & col_mask)));
+      if (SCALE) x[e] = fr_mul_shoup(x[e], ldg_tw(scale + ((col_base + idx) & col_mask)));
     }
     butterflies<R, DIF>(x, t_lo, s, q, W);
 #pragma unroll
@@ -125,7 +127,7 @@ __device__ __forceinline__ void smem_pass(const uint4* slo, const uint4* shi, ui
 
 template <int MAXR, bool DIF, bool SCALE>
 __device__ __forceinline__ void smem_pass_r(int r, const uint4* slo, const uint4* shi, uint4* dlo, uint4* dhi, int s,
-                                            int q, const Fr* W, const Fr* scale, uint32_t col_base, uint32_t col_mask,
+                                            int q, const FrTw* W, const FrTw* scale, uint32_t col_base, uint32_t col_mask,
                                             int E, int NT) {
   if (MAXR >= 3 && r == 3) smem_pass<(MAXR >= 3 ? 3 : 2), DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
   else if (r == 2) smem_pass<2, DIF, SCALE>(slo, shi, dlo, dhi, s, q, W, scale, col_base, col_mask, E, NT);
@@ -147,10 +149,11 @@ struct LocalArgs {
   int l;                // local stages = min(q, LOG_E)
   int rho;              // cosets (MODE 0)
   Fr* plane0;           // MODE 0: if non-null, also store the input here (only when `in` is the message)
-  const Fr* w_fwd;      // order-2^l tables (compact: every local stage indexes a dense 2^(l-1)-entry array)
-  const Fr* w_inv;
-  const Fr* scale;
-  Fr kinv;              // MODE 1: 1/k
+  const FrTw* w_fwd;    // order-2^l tables (compact: every local stage indexes a dense 2^(l-1)-entry array)
+  const FrTw* w_inv;
+  const FrTw* scale;
+  FrTw kinv;            // MODE 1: 1/k
+  int final;            // MODE 0: the coset values leaving this kernel are finished codeword elements (q == l)
   int mapped;           // MODE 0: 1 = finished elements (and the plane-0 copy) go through `map`
   int copy0;            // MODE 0, mapped: also store the input as plane 0
   OutMap map;
@@ -163,9 +166,9 @@ __device__ __forceinline__ void st_mapped(const LocalArgs& a, uint32_t s, unsign
 }
 
 // MODE 0: encode (iNTT tail + all cosets).  MODE 1: iNTT tail only, scaled, natural-order output.
-template <int LOG_E, int MAXR, int MINB, int MODE>
-__global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(const LocalArgs a) {
-  constexpr int E = 1 << LOG_E, NT = E >> MAXR;
+template <int LOG_E, int MAXR, int MINB, int MODE, int NT = (1 << (LOG_E - MAXR))>
+__global__ void __launch_bounds__(NT, MINB) ntt_local_kernel(const LocalArgs a) {
+  constexpr int E = 1 << LOG_E;
   extern __shared__ uint4 smem[];
   uint4 *Alo = smem, *Ahi = smem + E, *Blo = smem + 2 * E, *Bhi = smem + 3 * E;
   const unsigned long long f0 = (unsigned long long)blockIdx.x * E;
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
       if (f < a.total) {
         const uint32_t col = (uint32_t)(f & col_mask);
         const uint32_t nat = __brev(col) >> (32 - a.q);
-        st_fr(a.out + (f - col) + nat, fr_mul(lds_fr(Alo, Ahi, i), a.kinv));
+        st_fr(a.out + (f - col) + nat, fr_normalize_2r(fr_mul_shoup(lds_fr(Alo, Ahi, i), a.kinv)));
       }
     }
     return;
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
 
   // cosets 1 .. rho-1: scale (first pass, A -> B) then DIT stages 0 .. l-1 in B
   for (int cs = 1; cs < a.rho; cs++) {
-    const Fr* sc = a.scale + (size_t)(cs - 1) * ((size_t)1 << a.q);
+    const FrTw* sc = a.scale + (size_t)(cs - 1) * ((size_t)1 << a.q);
     for (int s = 0; s < a.l;) {
       const int r = pass_radix(a.l - s, MAXR);
       if (s == 0) smem_pass_r<MAXR, false, true>(r, Alo, Ahi, Blo, Bhi, 0, a.l, a.w_fwd, sc, col_base, col_mask, E, NT);
@@ -237,17 +240,19 @@ __global__ void __launch_bounds__(1 << (LOG_E - MAXR), MINB) ntt_local_kernel(co
     Fr* dst = a.out + (cs - 1) * a.plane_stride + f0;
     for (int i = threadIdx.x; i < E; i += NT)
       if (f0 + i < a.total) {
-        if (a.mapped) st_mapped(a, cs, f0 + i, lds_fr(Blo, Bhi, i));
-        else st_fr(dst + i, lds_fr(Blo, Bhi, i));
+        Fr v = lds_fr(Blo, Bhi, i);
+        if (a.final) v = fr_normalize(v);
+        if (a.mapped) st_mapped(a, cs, f0 + i, v);
+        else st_fr(dst + i, v);
       }
     __syncthreads();
   }
 }
 
 // register-only radix-2^R pass over global memory for the stages s..s+R-1 (s >= local size) of every row
-template <int R, bool DIF>
-__global__ void __launch_bounds__(256) ntt_global_pass_kernel(const Fr* in, Fr* out, Fr* copy_out, int q, int s,
-                                                              const Fr* __restrict__ W) {
+template <int R, bool DIF, int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) ntt_global_pass_kernel(const Fr* in, Fr* out, Fr* copy_out, int q, int s,
+                                                              const FrTw* __restrict__ W, int final) {
   const uint32_t g = blockIdx.y * blockDim.x + threadIdx.x;
   if (g >= (1u << (q - R))) return;
   const size_t off = (size_t)blockIdx.x << q;
@@ -265,7 +270,13 @@ __global__ void __launch_bounds__(256) ntt_global_pass_kernel(const Fr* in, Fr* 
     for (int e = 0; e < (1 << R); e++) st_fr(copy_out + off + (base | ((uint32_t)e << s)), x[e]);
   }
   if (nz == 0 && in == out) return;  // zeros stay zeros
-  if (nz != 0) butterflies<R, DIF>(x, t_lo, s, q, W);
+  if (nz != 0) {
+    butterflies<R, DIF>(x, t_lo, s, q, W);
+    if (final) {
+#pragma unroll
+      for (int e = 0; e < (1 << R); e++) x[e] = fr_normalize(x[e]);
+    }
+  }
 #pragma unroll
   for (int e = 0; e < (1 << R); e++) st_fr(out + off + (base | ((uint32_t)e << s)), x[e]);
 }
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(256) ntt_global_pass_kernel(const Fr* in, Fr* 
 // (plane 1 first) and the transformed values are final and go through the map
 template <int R, bool DIF, bool COPY0>
 __global__ void __launch_bounds__(256) ntt_global_pass_mapped_kernel(const Fr* in, Fr* out, int q, int s,
-                                                                     const Fr* __restrict__ W, const OutMap map,
+                                                                     const FrTw* __restrict__ W, const OutMap map,
                                                                      uint32_t rows_per_plane) {
   const uint32_t g = blockIdx.y * blockDim.x + threadIdx.x;
   if (g >= (1u << (q - R))) return;
@@ -295,12 +306,26 @@ __global__ void __launch_bounds__(256) ntt_global_pass_mapped_kernel(const Fr* i
 #pragma unroll
     for (int e = 0; e < (1 << R); e++) st_fr(outmap_ptr(map, 0, grow, base | ((uint32_t)e << s)), x[e]);
   }
-  if (nz != 0) butterflies<R, DIF>(x, t_lo, s, q, W);
+  if (nz != 0) {
+    butterflies<R, DIF>(x, t_lo, s, q, W);
+    if (!COPY0) {  // finished codeword elements
+#pragma unroll
+      for (int e = 0; e < (1 << R); e++) x[e] = fr_normalize(x[e]);
+    }
+  }
 #pragma unroll
   for (int e = 0; e < (1 << R); e++) {
     if (COPY0) st_fr(out + off + (base | ((uint32_t)e << s)), x[e]);
     else st_fr(outmap_ptr(map, plane, grow, base | ((uint32_t)e << s)), x[e]);
   }
+}
+
+// table generation: p = floor(w 2^256 / r) for every entry
+__global__ void fill_quotients_kernel(FrTw* t, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr p = fr_shoup_quotient(ld_fr(&t[i].w));
+  st_fr(&t[i].p, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -312,8 +337,8 @@ static uint32_t bitrev_host(uint32_t x, int bits) {
   return r;
 }
 
-int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out) {
-  auto key = std::make_pair(log_k, rho_inv);
+int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool plain) {
+  auto key = std::make_pair(log_k, rho_inv | (plain ? 1 << 16 : 0));
   auto it = ctx->tables.find(key);
   if (it != ctx->tables.end()) {
     *out = &it->second;
@@ -325,12 +350,20 @@ int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out) {
   if ((1 << log_rho) != rho_inv || rho_inv < 1 || log_k + log_rho > 28)
     return set_error(ctx, ERR_INVALID, "rho_inv must be a power of two with n <= 2^28");
   const size_t k = (size_t)1 << log_k, half = k / 2 ? k / 2 : 1;
-  std::vector<Fr> wf(half), wi(half), sc((size_t)(rho_inv - 1) * k);
+  // Montgomery-form powers on the host, then every entry becomes {plain integer, 0}; the quotient
+  // multipliers are filled in on the device (fill_quotients_kernel)
+  std::vector<FrTw> tab(2 * half + (size_t)(rho_inv - 1) * k);
+  FrTw* wf = tab.data();
+  FrTw* wi = wf + half;
+  FrTw* sc = wi + half;
   const Fr w = fr_root_of_unity(log_k), winv = fr_inv(w);
-  wf[0] = wi[0] = fr_one();
-  for (size_t i = 1; i < half; i++) {
-    wf[i] = fr_mul(wf[i - 1], w);
-    wi[i] = fr_mul(wi[i - 1], winv);
+  Fr a = fr_one(), b = fr_one();
+  for (size_t i = 0; i < half; i++) {
+    wf[i].w = fr_from_mont(a);
+    wi[i].w = fr_from_mont(b);
+    wf[i].p = wi[i].p = fr_zero();
+    a = fr_mul(a, w);
+    b = fr_mul(b, winv);
   }
   const Fr g = fr_root_of_unity(log_k + log_rho);
   const Fr kinv = fr_inv(fr_from_u64(k));
@@ -340,19 +373,28 @@ int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out) {
     gs = fr_mul(gs, g);  // g^s
     pw[0] = kinv;
     for (size_t i = 1; i < k; i++) pw[i] = fr_mul(pw[i - 1], gs);
-    for (size_t pos = 0; pos < k; pos++) sc[(size_t)(s - 1) * k + pos] = pw[bitrev_host((uint32_t)pos, log_k)];
+    for (size_t pos = 0; pos < k; pos++) {
+      FrTw& e = sc[(size_t)(s - 1) * k + pos];
+      e.w = fr_from_mont(pw[bitrev_host((uint32_t)pos, log_k)]);
+      if (plain) e.w = fr_from_mont(e.w);  // extra R^-1: Montgomery-form input -> plain-integer coset values
+      e.p = fr_zero();
+    }
   }
   NttTables t;
   t.log_k = log_k;
   t.rho_inv = rho_inv;
-  LG_CUDA(ctx, cudaMalloc(&t.w_fwd, half * sizeof(Fr)));
-  LG_CUDA(ctx, cudaMalloc(&t.w_inv, half * sizeof(Fr)));
-  LG_CUDA(ctx, cudaMalloc(&t.scale, (sc.size() ? sc.size() : 1) * sizeof(Fr)));
-  LG_CUDA(ctx, cudaMemcpyAsync(t.w_fwd, wf.data(), half * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  LG_CUDA(ctx, cudaMemcpyAsync(t.w_inv, wi.data(), half * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  if (!sc.empty())
-    LG_CUDA(ctx, cudaMemcpyAsync(t.scale, sc.data(), sc.size() * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host vectors die at scope exit
+  t.kinv.w = fr_from_mont(kinv);
+  t.kinv.p = fr_shoup_quotient(t.kinv.w);
+  FrTw* dev;
+  LG_CUDA(ctx, cudaMalloc(&dev, tab.size() * sizeof(FrTw)));
+  LG_CUDA(ctx, cudaMemcpyAsync(dev, tab.data(), tab.size() * sizeof(FrTw), cudaMemcpyHostToDevice, ctx->stream));
+  fill_quotients_kernel<<<(unsigned)((tab.size() + 127) / 128), 128, 0, ctx->stream>>>(dev, tab.size());
+  ctx->launches++;
+  LG_CUDA(ctx, cudaGetLastError());
+  LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vector dies at scope exit
+  t.w_fwd = dev;
+  t.w_inv = dev + half;
+  t.scale = dev + 2 * half;
   auto ins = ctx->tables.emplace(key, t);
   *out = &ins.first->second;
   return OK;
@@ -363,35 +405,48 @@ constexpr int kMaxR = 2;   // radix-4 passes: 256 threads x 4 elements, <= 85 re
 constexpr int kMinB = 3;   // (measured best of the four variants below: 131 ms vs 138/164/158 ms at 16388 x 8192)
 
 template <int R, bool DIF>
-static int launch_global_pass(Ctx* ctx, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s, const Fr* W) {
+static int launch_global_pass(Ctx* ctx, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s, const FrTw* W,
+                              int final) {
   const uint32_t groups = 1u << (q - R);
-  const uint32_t bs = groups < 256 ? groups : 256;
-  dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
-  ntt_global_pass_kernel<R, DIF><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W);
+  static int mode = -1;  // LG_GP_BLOCK=256 selects the 256-thread CTAs (tuning hook)
+  if (mode < 0) {
+    const char* e = getenv("LG_GP_BLOCK");
+    mode = (e && atoi(e) == 256) ? 1 : 0;
+  }
+  if (mode == 1) {
+    const uint32_t bs = groups < 256 ? groups : 256;
+    dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
+    ntt_global_pass_kernel<R, DIF, 256, 1><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W, final);
+  } else {
+    // 128 threads x 3 CTAs per SM: room for the radix-8 register tile (8 elements + a 16-register table entry)
+    const uint32_t bs = groups < 128 ? groups : 128;
+    dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
+    ntt_global_pass_kernel<R, DIF, 128, 3><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W, final);
+  }
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
 }
 template <bool DIF>
 static int launch_global_pass_r(Ctx* ctx, int r, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s,
-                                const Fr* W) {
-  if (r == 3) return launch_global_pass<3, DIF>(ctx, in, out, copy_out, rows, q, s, W);
-  if (r == 2) return launch_global_pass<2, DIF>(ctx, in, out, copy_out, rows, q, s, W);
-  return launch_global_pass<1, DIF>(ctx, in, out, copy_out, rows, q, s, W);
+                                const FrTw* W, int final = 0) {
+  if (r == 3) return launch_global_pass<3, DIF>(ctx, in, out, copy_out, rows, q, s, W, final);
+  if (r == 2) return launch_global_pass<2, DIF>(ctx, in, out, copy_out, rows, q, s, W, final);
+  return launch_global_pass<1, DIF>(ctx, in, out, copy_out, rows, q, s, W, final);
 }
 
-template <int MAXR, int MINB, int MODE>
+template <int MAXR, int MINB, int MODE, int NT = (1 << (kLogE - MAXR))>
 static int launch_local_v(Ctx* ctx, const LocalArgs& a) {
   constexpr int E = 1 << kLogE;
   const size_t smem = 4 * E * sizeof(uint4);
   static bool configured = false;
   if (!configured) {
-    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_local_kernel<kLogE, MAXR, MINB, MODE>,
+    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_local_kernel<kLogE, MAXR, MINB, MODE, NT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const unsigned long long ctas = (a.total + E - 1) / E;
-  ntt_local_kernel<kLogE, MAXR, MINB, MODE><<<(unsigned)ctas, E >> MAXR, smem, ctx->stream>>>(a);
+  ntt_local_kernel<kLogE, MAXR, MINB, MODE, NT><<<(unsigned)ctas, NT, smem, ctx->stream>>>(a);
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
@@ -414,6 +469,7 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
       case 1: return launch_local_v<2, 2, MODE>(ctx, a);   // radix-4, 2 CTAs/SM (<= 128 regs)
       case 2: return launch_local_v<3, 3, MODE>(ctx, a);   // radix-8, 128 threads, 3 CTAs/SM (<= 168 regs)
       case 3: return launch_local_v<3, 2, MODE>(ctx, a);   // radix-8, 128 threads, 2 CTAs/SM
+      case 4: return launch_local_v<2, 3, MODE, 128>(ctx, a);  // radix-4, 128 threads x 2 groups, 3 CTAs/SM (<= 168 regs)
       default: break;
     }
   }
@@ -421,7 +477,7 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
 }
 
 template <int R, bool DIF, bool COPY0>
-static int launch_global_pass_mapped(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int q, int s, const Fr* W,
+static int launch_global_pass_mapped(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int q, int s, const FrTw* W,
                                      const OutMap& map, uint32_t rows_per_plane) {
   const uint32_t groups = 1u << (q - R);
   const uint32_t bs = groups < 256 ? groups : 256;
@@ -432,18 +488,19 @@ static int launch_global_pass_mapped(Ctx* ctx, const Fr* in, Fr* out, size_t row
   return OK;
 }
 template <bool DIF, bool COPY0>
-static int launch_global_pass_mapped_r(Ctx* ctx, int r, const Fr* in, Fr* out, size_t rows, int q, int s, const Fr* W,
+static int launch_global_pass_mapped_r(Ctx* ctx, int r, const Fr* in, Fr* out, size_t rows, int q, int s, const FrTw* W,
                                        const OutMap& map, uint32_t rows_per_plane) {
   if (r == 3) return launch_global_pass_mapped<3, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
   if (r == 2) return launch_global_pass_mapped<2, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
   return launch_global_pass_mapped<1, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
 }
 
-int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets, const OutMap* map) {
+int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets, const OutMap* map,
+                bool plain_cosets) {
   if (rows == 0) return OK;
   if ((rows << log_k) >= ((size_t)1 << 42) || rows >= ((size_t)1 << 31)) return set_error(ctx, ERR_INVALID, "matrix too large");
   const NttTables* t;
-  LG_TRY(get_tables(ctx, log_k, rho_inv, &t));
+  LG_TRY(get_tables(ctx, log_k, rho_inv, &t, plain_cosets));
   const int q = log_k, l = q < kLogE ? q : kLogE;
   const NttTables* tl = t;
   if (l != q) LG_TRY(get_tables(ctx, l, 1, &tl));
@@ -458,6 +515,7 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
   a.w_fwd = tl->w_fwd;
   a.w_inv = tl->w_inv;
   a.scale = t->scale;
+  a.final = (q == l) ? 1 : 0;
   if (map) a.map = *map;
   phase_mark(ctx, PH_BEGIN);
   if (q > l) {
@@ -495,7 +553,7 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
       if (map && s + r == q)
         LG_TRY((launch_global_pass_mapped_r<false, false>(ctx, r, p, nullptr, prow, q, s, t->w_fwd, *map, (uint32_t)rows)));
       else
-        LG_TRY(launch_global_pass_r<false>(ctx, r, p, p, nullptr, prow, q, s, t->w_fwd));
+        LG_TRY(launch_global_pass_r<false>(ctx, r, p, p, nullptr, prow, q, s, t->w_fwd, s + r == q ? 1 : 0));
       s += r;
     }
     phase_mark(ctx, PH_NTT_STRIDED_FWD);
@@ -521,7 +579,7 @@ int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k) {
   a.w_fwd = tl->w_fwd;
   a.w_inv = tl->w_inv;
   a.scale = t->scale;
-  a.kinv = fr_inv(fr_from_u64((uint64_t)1 << q));
+  a.kinv = t->kinv;
   if (q > l) {
     void* tmp;
     LG_TRY(ctx_scratch(ctx, total * sizeof(Fr), &tmp));

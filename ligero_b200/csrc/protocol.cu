@@ -200,7 +200,9 @@ int expand_fr(Ctx* ctx, const uint8_t seed[32], size_t count, Fr* out_dev) {
 // grid = (k / 128, slabs): each CTA owns 128 columns of one slab of rows; partial[slab][c] is reduced
 // by col_reduce_final.  Reads are fully coalesced (a warp reads 1 KiB of one row).
 // ------------------------------------------------------------------------------------------------
-template <int MODE>
+// PLAIN: X (Y, Z) hold plain integers (coset plane >= 1 of a committed matrix): products with a Montgomery-form
+// weight then come out plain as well and col_reduce_final puts the R back; MODE 2 first lifts x so that x*y is plain.
+template <int MODE, bool PLAIN>
 __global__ void __launch_bounds__(128) col_reduce_kernel(const Fr* __restrict__ W, const Fr* __restrict__ X,
                                                          const Fr* __restrict__ Y, const Fr* __restrict__ Z, size_t rows,
                                                          size_t k, size_t rows_per_slab, Fr* __restrict__ partial) {
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(128) col_reduce_kernel(const Fr* __restrict__ 
       term = fr_mul(x, p_ld(W + i * k + c));
     } else {
       const Fr y = p_ld(Y + i * k + c), z = p_ld(Z + i * k + c);
-      term = fr_mul(fr_sub(fr_mul(x, y), z), p_ld(W + i));
+      term = fr_mul(fr_sub(fr_mul(PLAIN ? fr_mul(x, fr_r2()) : x, y), z), p_ld(W + i));
     }
     acc = fr_add(acc, term);
   }
@@ -227,17 +229,18 @@ __global__ void __launch_bounds__(128) col_reduce_kernel(const Fr* __restrict__ 
 
 // out[c * out_stride + out_offset] = sum_slab partial[slab][c]
 __global__ void col_reduce_final_kernel(const Fr* __restrict__ partial, size_t k, size_t slabs, Fr* __restrict__ out,
-                                        size_t out_stride, size_t out_offset) {
+                                        size_t out_stride, size_t out_offset, int to_mont) {
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= k) return;
   Fr acc = p_ld(partial + c);
   for (size_t s = 1; s < slabs; s++) acc = fr_add(acc, p_ld(partial + s * k + c));
+  if (to_mont) acc = fr_mul(acc, fr_r2());
   p_st(out + c * out_stride + out_offset, acc);
 }
 
 // mode as above; `out` gets k values at stride/offset (so two calls can interleave even/odd points)
 int col_reduce(Ctx* ctx, int mode, const Fr* W, const Fr* X, const Fr* Y, const Fr* Z, size_t rows, size_t k, Fr* out,
-               size_t out_stride, size_t out_offset) {
+               size_t out_stride, size_t out_offset, bool x_plain) {
   if (rows == 0 || k == 0) return set_error(ctx, ERR_INVALID, "empty reduction");
   // enough slabs to fill the machine: ~8 CTAs (of 128 threads) per SM
   const size_t col_ctas = (k + 127) / 128;
@@ -251,12 +254,16 @@ int col_reduce(Ctx* ctx, int mode, const Fr* W, const Fr* X, const Fr* Y, const 
   Fr* partial;
   LG_CUDA(ctx, cudaMallocAsync(&partial, slabs * k * sizeof(Fr), ctx->stream));
   dim3 grid((unsigned)col_ctas, (unsigned)slabs);
-  switch (mode) {
-    case 0: col_reduce_kernel<0><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
-    case 1: col_reduce_kernel<1><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
-    default: col_reduce_kernel<2><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
+  switch (mode * 2 + (x_plain ? 1 : 0)) {
+    case 0: col_reduce_kernel<0, false><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
+    case 1: col_reduce_kernel<0, true><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
+    case 2: col_reduce_kernel<1, false><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
+    case 3: col_reduce_kernel<1, true><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
+    case 4: col_reduce_kernel<2, false><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
+    default: col_reduce_kernel<2, true><<<grid, 128, 0, ctx->stream>>>(W, X, Y, Z, rows, k, rows_per_slab, partial); break;
   }
-  col_reduce_final_kernel<<<(unsigned)col_ctas, 128, 0, ctx->stream>>>(partial, k, slabs, out, out_stride, out_offset);
+  col_reduce_final_kernel<<<(unsigned)col_ctas, 128, 0, ctx->stream>>>(partial, k, slabs, out, out_stride, out_offset,
+                                                                     x_plain ? 1 : 0);
   ctx->launches += 2;
   LG_CUDA(ctx, cudaFreeAsync(partial, ctx->stream));
   LG_CUDA(ctx, cudaGetLastError());
@@ -305,7 +312,9 @@ __global__ void gather_columns_kernel(const Fr* __restrict__ u, size_t rows, int
   for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < tot; f += (size_t)gridDim.x * blockDim.x) {
     const size_t q = f / rows, i = f % rows;
     const size_t j = idx[q], s = j % rho, c = j / rho;
-    p_st(out + f, p_ld(u + s * rows * k + i * k + c));
+    Fr x = p_ld(u + s * rows * k + i * k + c);
+    if (s) x = fr_mul(x, fr_r2());  // coset planes hold plain integers (Matrix): back to Montgomery form
+    p_st(out + f, x);
   }
 }
 // sib[q] = leaf[idx ^ 1]; auth[q][d] for d = 0 .. log2(n)-2, root side first
