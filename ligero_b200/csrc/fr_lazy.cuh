@@ -84,12 +84,35 @@ LG_HD Fr fr_mul_shoup(const Fr& y, const FrTw& tw) {
                  w6 = tw.w.v[6], w7 = tw.w.v[7];
   const uint32_t p0 = tw.p.v[0], p1 = tw.p.v[1], p2 = tw.p.v[2], p3 = tw.p.v[3], p4 = tw.p.v[4], p5 = tw.p.v[5],
                  p6 = tw.p.v[6], p7 = tw.p.v[7];
-#include "fr_shoup_body.inc"
+#include "fr_shoup_body_q.inc"
+#include "fr_shoup_body_t.inc"
   (void)hx; (void)he6;
   Fr t;
   t.v[0] = e0; t.v[1] = e1; t.v[2] = e2; t.v[3] = e3; t.v[4] = e4; t.v[5] = e5; t.v[6] = e6; t.v[7] = e7;
   return t;
 }
+
+#ifdef __CUDACC__
+// The same product with the table entry still in memory: the quotient multiplier p is loaded first, the
+// constant w only once the quotient is done, so a thread never holds both halves (8 registers less at the
+// peak of the radix-4 shared-memory passes, which run at 80 registers per thread).
+__device__ __forceinline__ Fr fr_mul_shoup_ld(const Fr& y, const FrTw* __restrict__ tw) {
+  const uint32_t y0 = y.v[0], y1 = y.v[1], y2 = y.v[2], y3 = y.v[3], y4 = y.v[4], y5 = y.v[5], y6 = y.v[6], y7 = y.v[7];
+  const uint4* tp = reinterpret_cast<const uint4*>(tw);
+  uint32_t p0, p1, p2, p3, p4, p5, p6, p7;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p0), "=r"(p1), "=r"(p2), "=r"(p3) : "l"(tp + 2));
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p4), "=r"(p5), "=r"(p6), "=r"(p7) : "l"(tp + 3));
+#include "fr_shoup_body_q.inc"
+  uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "l"(tp));
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "l"(tp + 1));
+#include "fr_shoup_body_t.inc"
+  (void)hx; (void)he6;
+  Fr t;
+  t.v[0] = e0; t.v[1] = e1; t.v[2] = e2; t.v[3] = e3; t.v[4] = e4; t.v[5] = e5; t.v[6] = e6; t.v[7] = e7;
+  return t;
+}
+#endif
 
 // plain 256-bit add (callers guarantee no overflow)
 LG_HD Fr lz_add(const Fr& a, const Fr& b) {
@@ -194,6 +217,20 @@ LG_HD void lz_bfly_dit(Fr& X, Fr& Y, const FrTw& tw) {
   Y = lz_add(X, lz_2r_minus(T));
   X = lz_add(X, T);
 }
+#ifdef __CUDACC__
+__device__ __forceinline__ void lz_bfly_dit_ld(Fr& X, Fr& Y, const FrTw* __restrict__ tw) {
+  lz_csub2r(X);
+  const Fr T = fr_mul_shoup_ld(Y, tw);
+  Y = lz_add(X, lz_2r_minus(T));
+  X = lz_add(X, T);
+}
+__device__ __forceinline__ void lz_bfly_dif_ld(Fr& X, Fr& Y, const FrTw* __restrict__ tw) {
+  const Fr D = lz_add(X, lz_3r_minus(Y));
+  X = lz_add(X, Y);
+  lz_csub2r(X);
+  Y = fr_mul_shoup_ld(D, tw);
+}
+#endif
 // forward butterfly with w = 1
 LG_HD void lz_bfly_dit1(Fr& X, Fr& Y) {
   lz_csub2r(X);

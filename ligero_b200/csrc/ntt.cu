@@ -73,7 +73,9 @@ __device__ __forceinline__ void sts_fr(uint4* lo, uint4* hi, uint32_t i, const F
 // Values stay lazily reduced between stages (fr_lazy.cuh): < 4r + d forward, < 2r + d inverse; whoever
 // stores a FINISHED element applies fr_normalize, so what reaches U is the canonical representative.
 // ------------------------------------------------------------------------------------------------
-template <int R, bool DIF>
+// LATE: load each half of a table entry only when the product needs it (fr_mul_shoup_ld) instead of holding the
+// whole 16-register entry across the butterflies that share it -- for the register-starved shared-memory passes
+template <int R, bool DIF, bool LATE = false>
 __device__ __forceinline__ void butterflies(Fr (&x)[1 << R], uint32_t t_lo, int s, int q,
                                             const FrTw* __restrict__ W) {
 #pragma unroll
@@ -89,6 +91,14 @@ __device__ __forceinline__ void butterflies(Fr (&x)[1 << R], uint32_t t_lo, int 
           const int e0 = el | (eh << (b + 1)), e1 = e0 | (1 << b);
           if (!DIF) lz_bfly_dit1(x[e0], x[e1]);
           else lz_bfly_dif1(x[e0], x[e1]);
+        }
+      } else if (LATE) {
+        const FrTw* wp = W + ((size_t)j << shift);
+#pragma unroll
+        for (int eh = 0; eh < (1 << (R - 1 - b)); eh++) {
+          const int e0 = el | (eh << (b + 1)), e1 = e0 | (1 << b);
+          if (!DIF) lz_bfly_dit_ld(x[e0], x[e1], wp);
+          else lz_bfly_dif_ld(x[e0], x[e1], wp);
         }
       } else {
         const FrTw w = ldg_tw(W + ((size_t)j << shift));
@@ -117,9 +127,9 @@ __device__ __forceinline__ void smem_pass(const uint4* slo, const uint4* shi, ui
     for (int e = 0; e < (1 << R); e++) {
       const uint32_t idx = base | ((uint32_t)e << s);
       x[e] = lds_fr(slo, shi, idx);
-      if (SCALE) x[e] = fr_mul_shoup(x[e], ldg_tw(scale + ((col_base + idx) & col_mask)));
+      if (SCALE) x[e] = fr_mul_shoup_ld(x[e], scale + ((col_base + idx) & col_mask));
     }
-    butterflies<R, DIF>(x, t_lo, s, q, W);
+    butterflies<R, DIF, true>(x, t_lo, s, q, W);
 #pragma unroll
     for (int e = 0; e < (1 << R); e++) sts_fr(dlo, dhi, base | ((uint32_t)e << s), x[e]);
   }
@@ -167,7 +177,7 @@ __device__ __forceinline__ void st_mapped(const LocalArgs& a, uint32_t s, unsign
 
 // MODE 0: encode (iNTT tail + all cosets).  MODE 1: iNTT tail only, scaled, natural-order output.
 template <int LOG_E, int MAXR, int MINB, int MODE, int NT = (1 << (LOG_E - MAXR))>
-__global__ void __launch_bounds__(NT, MINB) ntt_local_kernel(const LocalArgs a) {
+__global__ void __launch_bounds__(NT, MINB) ntt_local_kernel(const __grid_constant__ LocalArgs a) {
   constexpr int E = 1 << LOG_E;
   extern __shared__ uint4 smem[];
   uint4 *Alo = smem, *Ahi = smem + E, *Blo = smem + 2 * E, *Bhi = smem + 3 * E;
@@ -285,8 +295,8 @@ __global__ void __launch_bounds__(BS, MINB) ntt_global_pass_kernel(const Fr* in,
 // the transformed values go to the local `out`; otherwise `in` holds rows_per_plane rows per coset plane
 // (plane 1 first) and the transformed values are final and go through the map
 template <int R, bool DIF, bool COPY0>
-__global__ void __launch_bounds__(256) ntt_global_pass_mapped_kernel(const Fr* in, Fr* out, int q, int s,
-                                                                     const FrTw* __restrict__ W, const OutMap map,
+__global__ void __launch_bounds__(128, 3) ntt_global_pass_mapped_kernel(const Fr* in, Fr* out, int q, int s,
+                                                                     const FrTw* __restrict__ W, const __grid_constant__ OutMap map,
                                                                      uint32_t rows_per_plane) {
   const uint32_t g = blockIdx.y * blockDim.x + threadIdx.x;
   if (g >= (1u << (q - R))) return;
@@ -480,7 +490,7 @@ template <int R, bool DIF, bool COPY0>
 static int launch_global_pass_mapped(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int q, int s, const FrTw* W,
                                      const OutMap& map, uint32_t rows_per_plane) {
   const uint32_t groups = 1u << (q - R);
-  const uint32_t bs = groups < 256 ? groups : 256;
+  const uint32_t bs = groups < 128 ? groups : 128;
   dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
   ntt_global_pass_mapped_kernel<R, DIF, COPY0><<<grid, bs, 0, ctx->stream>>>(in, out, q, s, W, map, rows_per_plane);
   ctx->launches++;

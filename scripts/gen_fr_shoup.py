@@ -189,6 +189,7 @@ def main():
         b = b if b in init else "0"
         ch.add("addc.cc" if i < 7 else "addc", f"q{i}", a, b)
     emit_chain(ch, init)
+    split = len(out)
     # ---- T = (y*w + qhat*nr) mod W^8: accumulators e (pairs 0,2,4,6) / o (pairs 1,3,5 and limb 7) ----
     for (a_name, b_of) in (("y", lambda j: f"w{j}"), ("q", lambda j: "0x%08xu" % NR_LIMBS[j])):
         for i in range(8):
@@ -204,10 +205,14 @@ def main():
         op = "add.cc" if i == 1 else ("addc.cc" if i < 7 else "addc")
         ch.add(op, f"e{i}", f"e{i}", f"o{i}")
     emit_chain(ch, init)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "ligero_b200", "csrc", "fr_shoup_body.inc")
-    with open(path, "w") as f:
-        f.write("\n".join(out) + "\n")
-    print("wrote", os.path.normpath(path), len(out), "lines")
+    # two files: the quotient part needs only (y, p), the remainder part only (y, w, qhat) -- a caller may load the
+    # two halves of a table entry separately to keep fewer registers live
+    base = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "ligero_b200", "csrc")
+    for name, lines in (("fr_shoup_body_q.inc", out[:split]), ("fr_shoup_body_t.inc", [out[0]] + out[split:])):
+        path = os.path.join(base, name)
+        with open(path, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        print("wrote", os.path.normpath(path), len(lines), "lines")
 
 
 if __name__ == "__main__":

@@ -29,10 +29,10 @@ def _run(n, seed, tmp_path):
 
 
 def test_generated_body_is_current():
-    inc = os.path.join(ROOT, "ligero_b200", "csrc", "fr_shoup_body.inc")
-    before = open(inc).read()
+    incs = [os.path.join(ROOT, "ligero_b200", "csrc", n) for n in ("fr_shoup_body_q.inc", "fr_shoup_body_t.inc")]
+    before = [open(i).read() for i in incs]
     subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_fr_shoup.py")], check=True, capture_output=True)
-    assert open(inc).read() == before, "fr_shoup_body.inc is stale: run scripts/gen_fr_shoup.py"
+    assert [open(i).read() for i in incs] == before, "fr_shoup_body_*.inc are stale: run scripts/gen_fr_shoup.py"
 
 
 def test_shoup_product_and_lazy_butterflies(tmp_path):
