@@ -113,6 +113,17 @@ int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t
 
 /* device addresses of the resident arrays (stream-ordered interop with the caller's own kernels /
  * collectives): U in the plane layout, n*32 leaf bytes, (n-1)*32 node bytes (node 0 = root) */
+/* The same, for `nrows` local rows that are the CONSECUTIVE global rows [row_base, row_base + nrows) of the
+ * rows_total-row matrix: lets a rank encode its share block by block (X, then Y, Z, W). */
+int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, size_t row_base, size_t rows_total, size_t k,
+                           uint32_t rho_inv, void* const* shard_u, int world, uint64_t* cosets_scratch);
+/* Column hashing in row tiles (src/ligero/mod.rs:536-542, one BLAKE2s stream per column): hash rows
+ * [row0, row_end) of every column on the context's second stream, ordered after everything enqueued on the
+ * context stream so far; tiles must come in row order and cover [0, rows).  lg_matrix_hash_finish builds the
+ * tree (544-551) and orders the context stream after it.  Both are asynchronous unless root_out is given.
+ * Lets the hashing of the rows that have arrived overlap the encoding (and NVLink delivery) of the rest. */
+int lg_matrix_hash_rows(lg_matrix* m, size_t row0, size_t row_end);
+int lg_matrix_hash_finish(lg_matrix* m, uint8_t root_out[32]);
 void* lg_matrix_u_dev(const lg_matrix* m);
 void* lg_matrix_leaves_dev(const lg_matrix* m);
 void* lg_matrix_nodes_dev(const lg_matrix* m);

@@ -47,6 +47,10 @@ SIGNATURES = {
     "lg_ipc_close": (c_int, [c_void_p, c_void_p]),
     "lg_encode_sharded": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p), c_int, c_size_t,
                                   c_size_t, c_void_p]),
+    "lg_encode_sharded_rows": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_uint32,
+                                       POINTER(c_void_p), c_int, c_void_p]),
+    "lg_matrix_hash_rows": (c_int, [c_void_p, c_size_t, c_size_t]),
+    "lg_matrix_hash_finish": (c_int, [c_void_p, c_void_p]),
     "lg_matrix_u_dev": (c_void_p, [c_void_p]),
     "lg_matrix_leaves_dev": (c_void_p, [c_void_p]),
     "lg_matrix_nodes_dev": (c_void_p, [c_void_p]),

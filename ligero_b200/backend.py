@@ -234,6 +234,17 @@ class CommittedMatrix:
         """column hashing + tree, no synchronisation (root stays on the device)."""
         check(self.ctx.lib.lg_matrix_hash(self.handle, None), self.ctx.handle, "lg_matrix_hash")
 
+    def hash_rows(self, row0: int, row_end: int):
+        """lg_matrix_hash_rows: hash rows [row0, row_end) of every column on the second stream (tiles in row order)."""
+        check(self.ctx.lib.lg_matrix_hash_rows(self.handle, row0, row_end), self.ctx.handle, "lg_matrix_hash_rows")
+
+    def hash_finish(self) -> bytes:
+        """lg_matrix_hash_finish: tree over the leaves of the last tile; returns the root."""
+        root = np.zeros(32, dtype=np.uint8)
+        check(self.ctx.lib.lg_matrix_hash_finish(self.handle, _ptr(root)), self.ctx.handle, "lg_matrix_hash_finish")
+        self.root = bytes(root)
+        return self.root
+
     def hash(self) -> bytes:
         root = np.zeros(32, dtype=np.uint8)
         check(self.ctx.lib.lg_matrix_hash(self.handle, _ptr(root)), self.ctx.handle, "lg_matrix_hash")

@@ -69,7 +69,7 @@ __global__ void gather_rows_kernel(const Fr* __restrict__ u, size_t rows, int lo
     Fr x;
     x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
     x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
-    if (s) x = fr_mul(x, fr_r2());  // coset planes hold plain integers (Matrix): back to Montgomery form
+    x = fr_mul(x, fr_r2());  // the planes hold plain integers (Matrix): back to Montgomery form
     uint4* dst = reinterpret_cast<uint4*>(out + f);
     dst[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     dst[1] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
@@ -198,6 +198,26 @@ static int stage_input(lg_ctx* ctx, const uint64_t* src, size_t elems, const Fr*
   return OK;
 }
 
+// second stream (lowest priority: it only fills what the encoder leaves free) + per-column state for tile-wise hashing
+static int hash_pipeline_setup(Ctx* c, size_t n) {
+  if (!c->hash_stream) {
+    int lo = 0, hi = 0;
+    LG_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    LG_CUDA(c, cudaStreamCreateWithPriority(&c->hash_stream, cudaStreamNonBlocking, lo));
+    LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_encoded, cudaEventDisableTiming));
+    LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_hashed, cudaEventDisableTiming));
+  }
+  if (c->hash_state_words < hash_state_words(n)) {
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->hash_stream));
+    if (c->hash_state) cudaFree(c->hash_state);
+    c->hash_state = nullptr;
+    LG_CUDA(c, cudaMalloc(&c->hash_state, hash_state_words(n) * sizeof(uint32_t)));
+    c->hash_state_words = hash_state_words(n);
+  }
+  return OK;
+}
+
 // Row-tile pipeline of the commit.
 //  * host input: tile i+1 is uploaded on a copy stream while tile i is being encoded (pinned host memory makes
 //    the copies truly asynchronous; pageable memory still works);
@@ -221,21 +241,7 @@ static int encode_tiled(lg_matrix* h, const uint64_t* src, bool host, bool hash)
       LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
     }
   }
-  if (hash && !c->hash_stream) {
-    int lo = 0, hi = 0;
-    LG_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    LG_CUDA(c, cudaStreamCreateWithPriority(&c->hash_stream, cudaStreamNonBlocking, lo));
-    LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_encoded, cudaEventDisableTiming));
-    LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_hashed, cudaEventDisableTiming));
-  }
-  if (hash && c->hash_state_words < 10 * m.n) {
-    LG_CUDA(c, cudaStreamSynchronize(c->stream));
-    LG_CUDA(c, cudaStreamSynchronize(c->hash_stream));
-    if (c->hash_state) cudaFree(c->hash_state);
-    c->hash_state = nullptr;
-    LG_CUDA(c, cudaMalloc(&c->hash_state, 10 * m.n * sizeof(uint32_t)));
-    c->hash_state_words = 10 * m.n;
-  }
+  if (hash) LG_TRY(hash_pipeline_setup(c, m.n));
   if (host && c->stage_bytes < tile_bytes) {
     LG_CUDA(c, cudaStreamSynchronize(c->stream));
     LG_CUDA(c, cudaStreamSynchronize(c->copy_stream));
@@ -613,6 +619,69 @@ int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t
     cudaFree(to_free);
   }
   return s;
+}
+
+int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, size_t row_base, size_t rows_total, size_t k,
+                           uint32_t rho_inv, void* const* shard_u, int world, uint64_t* cosets_scratch) {
+  if (!ctx || !shard_u) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (world < 1 || world > kMaxRanks || (world & (world - 1))) return set_error(c, ERR_INVALID, "world must be a power of two <= 8");
+  if (k < 2 || (k & (k - 1)) || k % world) return set_error(c, ERR_INVALID, "k must be a power of two divisible by world");
+  if (row_base + nrows > rows_total) return set_error(c, ERR_INVALID, "row range out of bounds");
+  if (nrows == 0) return OK;
+  if (!msg_rows) return set_error(c, ERR_INVALID, "null input matrix");
+  int log_k = 0, log_w = 0;
+  while (((size_t)1 << log_k) < k) log_k++;
+  while ((1 << log_w) < world) log_w++;
+  if (log_k > 10 && !cosets_scratch) return set_error(c, ERR_INVALID, "rows longer than 1024 need the local coset scratch buffer");
+  OutMap map{};
+  for (int g = 0; g < world; g++) {
+    if (!shard_u[g]) return set_error(c, ERR_INVALID, "null shard pointer");
+    map.base[g] = (Fr*)shard_u[g];
+  }
+  map.log_kg = log_k - log_w;
+  map.m = map.m_g = (uint32_t)nrows;  // one block of consecutive global rows: grow(i) = row_base + i
+  map.i0 = (uint32_t)row_base;
+  map.rows_total = rows_total;
+  const Fr* dev;
+  void* to_free;
+  LG_TRY(stage_input(ctx, msg_rows, nrows * k, &dev, &to_free));
+  int s = encode_rows(c, dev, nrows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map, true);
+  if (to_free) {
+    cudaStreamSynchronize(c->stream);
+    cudaFree(to_free);
+  }
+  return s;
+}
+
+int lg_matrix_hash_rows(lg_matrix* h, size_t row0, size_t row_end) {
+  if (!h) return ERR_INVALID;
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  cudaSetDevice(c->device);
+  LG_TRY(hash_pipeline_setup(c, m.n));
+  // everything enqueued on the context stream so far (the rows of this tile) happens before the tile is hashed
+  LG_CUDA(c, cudaEventRecord(c->ev_encoded, c->stream));
+  LG_CUDA(c, cudaStreamWaitEvent(c->hash_stream, c->ev_encoded, 0));
+  return hash_columns_range(c, c->hash_stream, m.u, m.rows, m.log_k, m.rho_inv, row0, row_end, c->hash_state, m.leaves,
+                            h->owner->col_len_prefix);
+}
+
+int lg_matrix_hash_finish(lg_matrix* h, uint8_t root_out[32]) {
+  if (!h) return ERR_INVALID;
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  cudaSetDevice(c->device);
+  LG_TRY(hash_pipeline_setup(c, m.n));
+  LG_TRY(merkle_build(c, m.leaves, m.n, m.nodes, h->owner->leaf_len_prefix, c->hash_stream));
+  LG_CUDA(c, cudaEventRecord(c->ev_hashed, c->hash_stream));
+  LG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_hashed, 0));
+  if (root_out) {
+    LG_CUDA(c, cudaMemcpyAsync(root_out, m.nodes, 32, cudaMemcpyDeviceToHost, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return OK;
 }
 
 void* lg_matrix_u_dev(const lg_matrix* m) { return m ? (void*)m->m.u : nullptr; }

@@ -106,7 +106,7 @@ int lg_row_combine(lg_matrix* h, const uint64_t* r, uint64_t* out) {
   DevBuf res;
   LG_TRY(res.alloc(c, m.k * sizeof(Fr)));
   phase_mark(c, PH_BEGIN);
-  LG_TRY(col_reduce(c, 0, (const Fr*)rin.ptr, m.u, nullptr, nullptr, m.rows, m.k, (Fr*)res.p, 1, 0));  // plane 0 = U_pre
+  LG_TRY(col_reduce(c, 0, (const Fr*)rin.ptr, m.u, nullptr, nullptr, m.rows, m.k, (Fr*)res.p, 1, 0, true));  // plane 0 = U_pre
   phase_mark(c, PH_TESTS);
   LG_CUDA(c, cudaMemcpyAsync(out, res.p, m.k * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -196,9 +196,9 @@ static int linear_test_core(lg_matrix* h, Fr* r_a, uint64_t* coeffs_out, size_t*
   LG_TRY(encode_rows(c, r_a, m.rows, m.log_k, 2, nullptr, (Fr*)odd.p));
   phase_mark(c, PH_BEGIN);
   // q(zeta^(2c)) = sum_i r_a[i][c] U[i][rho c];   q(zeta^(2c+1)) = sum_i r_odd[i][c] U[i][rho c + rho/2]
-  LG_TRY(col_reduce(c, 1, r_a, m.u, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 0));
+  LG_TRY(col_reduce(c, 1, r_a, m.u, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 0, true));
   LG_TRY(col_reduce(c, 1, (const Fr*)odd.p, m.u + (size_t)(m.rho_inv / 2) * plane, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 1,
-                    true));  // coset planes of the committed matrix hold plain integers
+                    true));  // the planes of the committed matrix hold plain integers
   phase_mark(c, PH_TESTS);
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);
 }
@@ -246,7 +246,7 @@ int lg_quadratic_test(lg_matrix* h, const uint64_t* r_quad, uint64_t* coeffs_out
   phase_mark(c, PH_BEGIN);
   for (int half = 0; half < 2; half++) {
     const Fr* p = m.u + (size_t)(half ? m.rho_inv / 2 : 0) * plane;
-    LG_TRY(col_reduce(c, 2, (const Fr*)rin.ptr, p, p + mm * m.k, p + 2 * mm * m.k, mm, m.k, (Fr*)qhat.p, 2, half, half != 0));
+    LG_TRY(col_reduce(c, 2, (const Fr*)rin.ptr, p, p + mm * m.k, p + 2 * mm * m.k, mm, m.k, (Fr*)qhat.p, 2, half, true));
   }
   phase_mark(c, PH_TESTS);
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);

@@ -80,15 +80,21 @@ __device__ __forceinline__ void blake2s_init(uint32_t (&h)[8]) {
 // elements apart.  MONT: elements are in Montgomery form and are converted in registers.
 // The 64-byte blocks [b0, b1) of the column message are compressed; block b holds rows 2b and 2b+1
 // (shifted by the 8-byte length prefix, whose spill-over travels in c0/c1).  A column can therefore be
-// hashed in row tiles -- (h, c0, c1) is the whole carried state -- which lets the commit overlap the
-// hashing of one tile with the encoding of the next.  Rows at or beyond `row_lim` are not read.
+// hashed in row tiles: the carried state is (h, c0, c1) plus, when a tile ends on an odd row, that row's
+// element (`pend`, raw as stored in U), which opens the next tile's first block.  This is what lets a commit
+// overlap the hashing of one row tile with the encoding of the next (and, across GPUs, with the rows that
+// are still arriving over NVLink).  Rows at or beyond `row_lim` are not read.
+constexpr int kHashL2Ahead = 6;  // blocks (pairs of rows) prefetched into L2 ahead of the register prefetch
+
 template <bool PREFIX, bool MONT>
 __device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride, size_t rows, size_t row_lim, uint64_t b0,
-                                                   uint64_t b1, uint32_t (&h)[8], uint32_t& c0, uint32_t& c1) {
+                                                   uint64_t b1, bool have_pend, uint32_t (&h)[8], uint32_t& c0,
+                                                   uint32_t& c1, Fr& pend) {
   const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
   const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
   Fr n0 = fr_zero(), n1 = fr_zero();
-  if (2 * b0 < row_lim) n0 = ld_fr_g(col + 2 * b0 * stride);
+  if (have_pend) n0 = pend;
+  else if (2 * b0 < row_lim) n0 = ld_fr_g(col + 2 * b0 * stride);
   if (2 * b0 + 1 < row_lim) n1 = ld_fr_g(col + (2 * b0 + 1) * stride);
   for (uint64_t b = b0; b < b1; b++) {
     Fr e0 = n0, e1 = n1;
@@ -97,6 +103,12 @@ __device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride,
     n1 = fr_zero();
     if (r2 < row_lim) n0 = ld_fr_g(col + r2 * stride);          // prefetch the next block's two elements
     if (r2 + 1 < row_lim) n1 = ld_fr_g(col + (r2 + 1) * stride);
+    // ... and pull the rows of a few blocks further down into L2: consecutive rows of a column are a whole row
+    // pitch apart (new DRAM page, often a new TLB entry), and with few columns per SM nothing else hides that
+    if (r2 + 2 * kHashL2Ahead + 1 < row_lim) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (r2 + 2 * kHashL2Ahead) * stride));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (r2 + 2 * kHashL2Ahead + 1) * stride));
+    }
     if (MONT) {
       e0 = fr_from_mont(e0);
       e1 = fr_from_mont(e1);
@@ -117,6 +129,7 @@ __device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride,
     const uint64_t t = last ? total : 64 * (b + 1);
     blake2s_compress(h, m, t, last);
   }
+  pend = n0;  // row 2*b1 if the tile ends on it (odd row_lim), else unused
 }
 
 template <bool PREFIX, bool MONT>
@@ -125,11 +138,13 @@ __device__ __forceinline__ void hash_one_column(const Fr* col, size_t stride, si
   const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
   const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
   uint32_t c0 = (uint32_t)rows, c1 = (uint32_t)((uint64_t)rows >> 32);  // carry words (PREFIX): u64_le(R) first
-  hash_column_blocks<PREFIX, MONT>(col, stride, rows, rows, 0, nblocks, h, c0, c1);
+  Fr pend = fr_zero();
+  hash_column_blocks<PREFIX, MONT>(col, stride, rows, rows, 0, nblocks, false, h, c0, c1, pend);
 }
 
-// rows [row0, row_end) of every column; row0 even, row_end even unless it is `rows`.  `state` carries
-// (h[8], c0, c1) per physical column between tiles, word-major so a warp's accesses coalesce.
+// rows [row0, row_end) of every column.  `state` carries (h[8], c0, c1, pend[8]) per physical column between
+// tiles, word-major so a warp's accesses coalesce; the tile that ends at `rows` writes the leaves.
+constexpr int kHashStateWords = 18;
 template <bool PREFIX>
 __global__ void __launch_bounds__(64) hash_columns_kernel(const Fr* __restrict__ u, size_t rows, int log_k, int rho,
                                                           size_t row0, size_t row_end, uint32_t* __restrict__ state,
@@ -140,8 +155,9 @@ __global__ void __launch_bounds__(64) hash_columns_kernel(const Fr* __restrict__
   const size_t s = pc >> log_k, c = pc & (k - 1);
   const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
   const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
-  const bool first = row0 == 0, last = row_end >= rows;
+  const bool first = row0 == 0, last = row_end >= rows, have_pend = (row0 & 1) != 0;
   uint32_t h[8], c0, c1;
+  Fr pend = fr_zero();
   if (first) {
     blake2s_init(h);
     c0 = (uint32_t)rows;
@@ -151,20 +167,24 @@ __global__ void __launch_bounds__(64) hash_columns_kernel(const Fr* __restrict__
     for (int i = 0; i < 8; i++) h[i] = state[(size_t)i * ncols + pc];
     c0 = state[8 * ncols + pc];
     c1 = state[9 * ncols + pc];
+    if (have_pend) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) pend.v[i] = state[(size_t)(10 + i) * ncols + pc];
+    }
   }
-  // plane 0 is the caller's Montgomery-form message (converted in registers); the coset planes already hold
-  // the plain integers (Matrix).  With k >= 32 columns per plane the branch is warp-uniform
-  if (s == 0)
-    hash_column_blocks<PREFIX, true>(u + c, k, rows, row_end < rows ? row_end : rows, row0 / 2,
-                                     last ? nblocks : row_end / 2, h, c0, c1);
-  else
-    hash_column_blocks<PREFIX, false>(u + s * rows * k + c, k, rows, row_end < rows ? row_end : rows, row0 / 2,
-                                      last ? nblocks : row_end / 2, h, c0, c1);
+  const size_t lim = row_end < rows ? row_end : rows;
+  const uint64_t b0 = row0 / 2, b1 = last ? nblocks : row_end / 2;
+  // every plane of a committed matrix holds plain integers (Matrix): no conversion here
+  hash_column_blocks<PREFIX, false>(u + s * rows * k + c, k, rows, lim, b0, b1, have_pend, h, c0, c1, pend);
   if (!last) {
 #pragma unroll
     for (int i = 0; i < 8; i++) state[(size_t)i * ncols + pc] = h[i];
     state[8 * ncols + pc] = c0;
     state[9 * ncols + pc] = c1;
+    if (row_end & 1) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) state[(size_t)(10 + i) * ncols + pc] = pend.v[i];
+    }
     return;
   }
   uint4* dst = reinterpret_cast<uint4*>(leaves + 32 * ((size_t)rho * c + s));  // logical column rho*c + s
@@ -187,8 +207,8 @@ __global__ void hash_column_list_kernel(const Fr* __restrict__ cols, size_t rows
 
 int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u, size_t rows, int log_k, int rho_inv, size_t row0,
                        size_t row_end, uint32_t* state, uint8_t* leaves, bool len_prefix) {
-  if ((row0 & 1) || (row_end < rows && (row_end & 1)) || ((row0 > 0 || row_end < rows) && !state))
-    return set_error(ctx, ERR_INVALID, "column hashing tiles must start and end on even rows and carry a state buffer");
+  if (row0 >= row_end || row_end > rows || ((row0 > 0 || row_end < rows) && !state))
+    return set_error(ctx, ERR_INVALID, "column hashing tile out of range, or a partial tile without a state buffer");
   const size_t n = (size_t)rho_inv << log_k;
   const unsigned bs = 64;
   const unsigned grid = (unsigned)((n + bs - 1) / bs);
@@ -198,6 +218,8 @@ int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u, size_t rows, int 
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
 }
+
+size_t hash_state_words(size_t n) { return (size_t)kHashStateWords * n; }
 
 int hash_columns(Ctx* ctx, const Fr* u, size_t rows, int log_k, int rho_inv, uint8_t* leaves, bool len_prefix) {
   return hash_columns_range(ctx, ctx->stream, u, rows, log_k, rho_inv, 0, rows, nullptr, leaves, len_prefix);

@@ -92,11 +92,12 @@ int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool pla
 // ---- committed matrix ------------------------------------------------------------------------------
 // Physical layout of U (R x n, n = rho_inv*k) in HBM: rho_inv "coset planes", each R x k row-major:
 //     plane[s][i][c] = U[i][rho_inv*c + s] = p_i(g^s * omega_k^c)
-// plane 0 is the message itself (systematic positions, src/ligero/mod.rs:89), in the caller's Montgomery form.
-// Planes s >= 1 hold the PLAIN integers (a, not a*R): the column hash needs exactly those bytes, and the
-// encoder produces them for free by folding R^-1 into the coset scale table (the transform is linear), which
-// removes one Montgomery reduction per codeword element from the hash kernel.  Everything that reads U back
-// (openings, row read-back, the two test reductions on plane rho_inv/2) converts on the fly.
+// plane 0 is the message itself (systematic positions, src/ligero/mod.rs:89).
+// All planes hold the PLAIN integers (a, not the caller's Montgomery form a*R): the column hash needs exactly
+// those bytes.  The encoder produces the coset planes that way for free by folding R^-1 into the coset scale
+// table (the transform is linear) and converts plane 0 while copying it, so the hash kernel -- a latency-bound
+// chain per column -- carries no Montgomery reduction at all.  Everything that reads U back (openings, row
+// read-back, the test reductions) converts on the fly.
 struct Matrix {
   Ctx* ctx = nullptr;
   size_t rows = 0;      // R
@@ -137,7 +138,7 @@ __device__ __forceinline__ Fr* outmap_ptr(const OutMap& o, uint32_t s, uint32_t 
 // plane0 (nullable) receives a copy of the message; cosets receives the rho_inv-1 planes s = 1..rho_inv-1
 // map (nullable): final destination of every element (multi-GPU); `cosets` is then only the local
 // intermediate of rows longer than one CTA tile and plane0 is ignored
-// plain_cosets: coset planes as plain integers (the committed matrix, see Matrix) instead of Montgomery form
+// plain_cosets: all planes (incl. the plane-0 copy) as plain integers (the committed matrix, see Matrix)
 int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets,
                 const OutMap* map = nullptr, bool plain_cosets = false);
 // protocol.cu
@@ -157,8 +158,10 @@ int hash_columns(Ctx* ctx, const Fr* u_planes, size_t rows, int log_k, int rho_i
 // Merkle tree (a6)
 int merkle_build(Ctx* ctx, const uint8_t* leaves, size_t n, uint8_t* nodes, bool leaf_len_prefix,
                  cudaStream_t st = nullptr);
-// the same column hash over the row tile [row0, row_end) only (even boundaries), carrying the BLAKE2s state
-// of every column in `state` (10 x n words) between tiles; the tile that ends at `rows` writes the leaves
+// the same column hash over the row tile [row0, row_end) only, carrying the BLAKE2s state of every column in
+// `state` (hash_state_words(n) words) between tiles; tiles come in row order and the one that ends at `rows`
+// writes the leaves
+size_t hash_state_words(size_t n);
 int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u_planes, size_t rows, int log_k, int rho_inv, size_t row0,
                        size_t row_end, uint32_t* state, uint8_t* leaves, bool len_prefix);
 // BLAKE2s of `count` explicit columns (each `rows` contiguous Montgomery elements)

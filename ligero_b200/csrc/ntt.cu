@@ -166,6 +166,7 @@ struct LocalArgs {
   int final;            // MODE 0: the coset values leaving this kernel are finished codeword elements (q == l)
   int mapped;           // MODE 0: 1 = finished elements (and the plane-0 copy) go through `map`
   int copy0;            // MODE 0, mapped: also store the input as plane 0
+  int plain0;           // MODE 0: the plane-0 copy is stored as plain integers (from_mont), like the coset planes
   OutMap map;
 };
 
@@ -193,10 +194,10 @@ __global__ void __launch_bounds__(NT, MINB) ntt_local_kernel(const __grid_consta
     nz |= fr_or(x);
     sts_fr(Alo, Ahi, i, x);
     if (MODE == 0 && f < a.total) {
-      if (a.mapped) {
-        if (a.copy0) st_mapped(a, 0, f, x);
-      } else if (a.plane0) {
-        st_fr(a.plane0 + f, x);
+      if (a.mapped ? a.copy0 != 0 : a.plane0 != nullptr) {
+        const Fr x0 = a.plain0 ? fr_from_mont(x) : x;
+        if (a.mapped) st_mapped(a, 0, f, x0);
+        else st_fr(a.plane0 + f, x0);
       }
     }
   }
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(NT, MINB) ntt_local_kernel(const __grid_consta
 // register-only radix-2^R pass over global memory for the stages s..s+R-1 (s >= local size) of every row
 template <int R, bool DIF, int BS, int MINB>
 __global__ void __launch_bounds__(BS, MINB) ntt_global_pass_kernel(const Fr* in, Fr* out, Fr* copy_out, int q, int s,
-                                                              const FrTw* __restrict__ W, int final) {
+                                                              const FrTw* __restrict__ W, int final, int copy_plain) {
   const uint32_t g = blockIdx.y * blockDim.x + threadIdx.x;
   if (g >= (1u << (q - R))) return;
   const size_t off = (size_t)blockIdx.x << q;
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(BS, MINB) ntt_global_pass_kernel(const Fr* in,
   }
   if (copy_out) {
 #pragma unroll
-    for (int e = 0; e < (1 << R); e++) st_fr(copy_out + off + (base | ((uint32_t)e << s)), x[e]);
+    for (int e = 0; e < (1 << R); e++)
+      st_fr(copy_out + off + (base | ((uint32_t)e << s)), (copy_plain && nz) ? fr_from_mont(x[e]) : x[e]);
   }
   if (nz == 0 && in == out) return;  // zeros stay zeros
   if (nz != 0) {
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(BS, MINB) ntt_global_pass_kernel(const Fr* in,
 template <int R, bool DIF, bool COPY0>
 __global__ void __launch_bounds__(128, 3) ntt_global_pass_mapped_kernel(const Fr* in, Fr* out, int q, int s,
                                                                      const FrTw* __restrict__ W, const __grid_constant__ OutMap map,
-                                                                     uint32_t rows_per_plane) {
+                                                                     uint32_t rows_per_plane, int copy_plain) {
   const uint32_t g = blockIdx.y * blockDim.x + threadIdx.x;
   if (g >= (1u << (q - R))) return;
   const size_t off = (size_t)blockIdx.x << q;
@@ -314,7 +316,8 @@ __global__ void __launch_bounds__(128, 3) ntt_global_pass_mapped_kernel(const Fr
   }
   if (COPY0) {
 #pragma unroll
-    for (int e = 0; e < (1 << R); e++) st_fr(outmap_ptr(map, 0, grow, base | ((uint32_t)e << s)), x[e]);
+    for (int e = 0; e < (1 << R); e++)
+      st_fr(outmap_ptr(map, 0, grow, base | ((uint32_t)e << s)), (copy_plain && nz) ? fr_from_mont(x[e]) : x[e]);
   }
   if (nz != 0) {
     butterflies<R, DIF>(x, t_lo, s, q, W);
@@ -416,7 +419,7 @@ constexpr int kMinB = 3;   // (measured best of the four variants below: 131 ms 
 
 template <int R, bool DIF>
 static int launch_global_pass(Ctx* ctx, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s, const FrTw* W,
-                              int final) {
+                              int final, int copy_plain) {
   const uint32_t groups = 1u << (q - R);
   static int mode = -1;  // LG_GP_BLOCK=256 selects the 256-thread CTAs (tuning hook)
   if (mode < 0) {
@@ -426,12 +429,12 @@ static int launch_global_pass(Ctx* ctx, const Fr* in, Fr* out, Fr* copy_out, siz
   if (mode == 1) {
     const uint32_t bs = groups < 256 ? groups : 256;
     dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
-    ntt_global_pass_kernel<R, DIF, 256, 1><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W, final);
+    ntt_global_pass_kernel<R, DIF, 256, 1><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W, final, copy_plain);
   } else {
     // 128 threads x 3 CTAs per SM: room for the radix-8 register tile (8 elements + a 16-register table entry)
     const uint32_t bs = groups < 128 ? groups : 128;
     dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
-    ntt_global_pass_kernel<R, DIF, 128, 3><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W, final);
+    ntt_global_pass_kernel<R, DIF, 128, 3><<<grid, bs, 0, ctx->stream>>>(in, out, copy_out, q, s, W, final, copy_plain);
   }
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
@@ -439,10 +442,10 @@ static int launch_global_pass(Ctx* ctx, const Fr* in, Fr* out, Fr* copy_out, siz
 }
 template <bool DIF>
 static int launch_global_pass_r(Ctx* ctx, int r, const Fr* in, Fr* out, Fr* copy_out, size_t rows, int q, int s,
-                                const FrTw* W, int final = 0) {
-  if (r == 3) return launch_global_pass<3, DIF>(ctx, in, out, copy_out, rows, q, s, W, final);
-  if (r == 2) return launch_global_pass<2, DIF>(ctx, in, out, copy_out, rows, q, s, W, final);
-  return launch_global_pass<1, DIF>(ctx, in, out, copy_out, rows, q, s, W, final);
+                                const FrTw* W, int final = 0, int copy_plain = 0) {
+  if (r == 3) return launch_global_pass<3, DIF>(ctx, in, out, copy_out, rows, q, s, W, final, copy_plain);
+  if (r == 2) return launch_global_pass<2, DIF>(ctx, in, out, copy_out, rows, q, s, W, final, copy_plain);
+  return launch_global_pass<1, DIF>(ctx, in, out, copy_out, rows, q, s, W, final, copy_plain);
 }
 
 template <int MAXR, int MINB, int MODE, int NT = (1 << (kLogE - MAXR))>
@@ -488,21 +491,21 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
 
 template <int R, bool DIF, bool COPY0>
 static int launch_global_pass_mapped(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int q, int s, const FrTw* W,
-                                     const OutMap& map, uint32_t rows_per_plane) {
+                                     const OutMap& map, uint32_t rows_per_plane, int copy_plain) {
   const uint32_t groups = 1u << (q - R);
   const uint32_t bs = groups < 128 ? groups : 128;
   dim3 grid((unsigned)rows, (groups + bs - 1) / bs);
-  ntt_global_pass_mapped_kernel<R, DIF, COPY0><<<grid, bs, 0, ctx->stream>>>(in, out, q, s, W, map, rows_per_plane);
+  ntt_global_pass_mapped_kernel<R, DIF, COPY0><<<grid, bs, 0, ctx->stream>>>(in, out, q, s, W, map, rows_per_plane, copy_plain);
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
 }
 template <bool DIF, bool COPY0>
 static int launch_global_pass_mapped_r(Ctx* ctx, int r, const Fr* in, Fr* out, size_t rows, int q, int s, const FrTw* W,
-                                       const OutMap& map, uint32_t rows_per_plane) {
-  if (r == 3) return launch_global_pass_mapped<3, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
-  if (r == 2) return launch_global_pass_mapped<2, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
-  return launch_global_pass_mapped<1, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane);
+                                       const OutMap& map, uint32_t rows_per_plane, int copy_plain = 0) {
+  if (r == 3) return launch_global_pass_mapped<3, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane, copy_plain);
+  if (r == 2) return launch_global_pass_mapped<2, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane, copy_plain);
+  return launch_global_pass_mapped<1, DIF, COPY0>(ctx, in, out, rows, q, s, W, map, rows_per_plane, copy_plain);
 }
 
 int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr* plane0, Fr* cosets, const OutMap* map,
@@ -526,6 +529,7 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
   a.w_inv = tl->w_inv;
   a.scale = t->scale;
   a.final = (q == l) ? 1 : 0;
+  a.plain0 = plain_cosets ? 1 : 0;
   if (map) a.map = *map;
   phase_mark(ctx, PH_BEGIN);
   if (q > l) {
@@ -536,9 +540,11 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
     for (int top = q; top > l;) {
       const int r = pass_radix(top - l), s = top - r;
       if (first && map)
-        LG_TRY((launch_global_pass_mapped_r<true, true>(ctx, r, src, (Fr*)tmp, rows, q, s, t->w_inv, *map, (uint32_t)rows)));
+        LG_TRY((launch_global_pass_mapped_r<true, true>(ctx, r, src, (Fr*)tmp, rows, q, s, t->w_inv, *map, (uint32_t)rows,
+                                                        plain_cosets ? 1 : 0)));
       else
-        LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, first ? plane0 : nullptr, rows, q, s, t->w_inv));
+        LG_TRY(launch_global_pass_r<true>(ctx, r, src, (Fr*)tmp, first ? plane0 : nullptr, rows, q, s, t->w_inv, 0,
+                                          plain_cosets ? 1 : 0));
       src = (const Fr*)tmp;
       first = false;
       top = s;

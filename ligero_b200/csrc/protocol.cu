@@ -313,7 +313,7 @@ __global__ void gather_columns_kernel(const Fr* __restrict__ u, size_t rows, int
     const size_t q = f / rows, i = f % rows;
     const size_t j = idx[q], s = j % rho, c = j / rho;
     Fr x = p_ld(u + s * rows * k + i * k + c);
-    if (s) x = fr_mul(x, fr_r2());  // coset planes hold plain integers (Matrix): back to Montgomery form
+    x = fr_mul(x, fr_r2());  // the planes hold plain integers (Matrix): back to Montgomery form
     p_st(out + f, x);
   }
 }

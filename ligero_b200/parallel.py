@@ -101,15 +101,25 @@ class ShardedCommitter:
     mode "fused" (default): the exchange is fused into the encode kernels -- the last NTT pass stores each
         finished element directly into the owning rank's column shard over NVLink peer memory (CUDA IPC
         mappings exchanged once at construction), so the transfer overlaps the butterflies and there is no
-        pack / all-to-all / unpack; one tiny NCCL all-reduce orders the ranks before hashing.
+        pack / all-to-all / unpack.  The four row blocks X, Y, Z, W are encoded one after the other; after
+        each, one tiny NCCL all-reduce tells every rank that the block has landed everywhere and the column
+        owner hashes those rows on its second stream WHILE the next block is encoded and delivered: a column
+        hash is a sequential chain per column (`pipeline=False` hashes after the last block instead; the
+        default picks by world size from measurements, see __init__).
     mode "nccl": encode locally, then pack -> NCCL all_to_all -> unpack (the plain-library baseline, and the
         plumbing the gloo tests cover).
     """
 
-    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int, mode: str = "fused"):
+    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int, mode: str = "fused", pipeline=None):
         assert world & (world - 1) == 0 and k % world == 0 and (rho * k // world) >= 2
         assert mode in ("fused", "nccl")
         self.ctx, self.m, self.k, self.rho, self.rank, self.world, self.mode = ctx, m, k, rho, rank, world, mode
+        if pipeline is None:
+            # measured on 8 x B200 (2^24-gate shape): the block pipeline wins at 2 GPUs (78.6 vs 81.9 ms) and loses
+            # at 4 and 8 (44.3 vs 41.7, 31.6 vs 26.2 ms), where the hash is a pure latency chain that the encoder's
+            # warps on the same SM slow down more than the overlap gains
+            pipeline = world <= 2
+        self.pipeline = bool(pipeline) and mode == "fused"
         self.slices = block_slices(m, world)
         i0, i1 = self.slices[rank]
         self.i0, self.m_g = i0, i1 - i0
@@ -188,6 +198,21 @@ class ShardedCommitter:
                 mark("exchange")
                 unpack_after_exchange(self.recv, self.u_cols, self.m, self.world, self.rho, self.kg)
                 mark("unpack")
+            elif self.pipeline:
+                lib, scratch = self.ctx.lib, (_ptr(self.scratch) if self.scratch is not None else None)
+                base = int(_ptr(msg_local).value or 0)
+                for b in range(4):                 # local rows are [X_g; Y_g; Z_g; W_g], 32 bytes per element
+                    off = b * self.m_g * self.k * 32
+                    check(lib.lg_encode_sharded_rows(self.ctx.handle, base + off if self.m_g else None, self.m_g,
+                                                     b * self.m + self.i0, 4 * self.m, self.k, self.rho,
+                                                     self.shard_ptrs, self.world, scratch),
+                          self.ctx.handle, "lg_encode_sharded_rows")
+                    dist.all_reduce(self.flag)      # block b has landed on every rank ...
+                    check(lib.lg_matrix_hash_rows(self.mat_cols.handle, b * self.m, (b + 1) * self.m),
+                          self.ctx.handle, "lg_matrix_hash_rows")   # ... and is hashed behind the next block
+                mark("encode+scatter over NVLink (column hashing of earlier blocks overlapped)")
+                check(lib.lg_matrix_hash_finish(self.mat_cols.handle, None), self.ctx.handle, "lg_matrix_hash_finish")
+                mark("hash tail+subtree")
             else:
                 check(self.ctx.lib.lg_encode_sharded(self.ctx.handle, _ptr(msg_local), self.m_g, self.k, self.rho,
                                                      self.shard_ptrs, self.world, self.m, self.i0,
@@ -196,8 +221,9 @@ class ShardedCommitter:
                 mark("encode+scatter over NVLink")
                 dist.all_reduce(self.flag)      # every rank's stores have landed before anyone hashes
                 mark("rank barrier")
-            self.mat_cols.hash_async()
-            mark("hash+subtree")
+            if not self.pipeline:
+                self.mat_cols.hash_async()
+                mark("hash+subtree")
             # subtree root = node 0 of the local tree (device -> device, stays on the stream)
             self._copy_root()
             dist.all_gather_into_tensor(self.roots.view(-1), self.my_root)
@@ -226,8 +252,9 @@ class ShardedCommitter:
     def bench(ctx, R: int, k: int, rho: int, args, rank: int, world: int) -> dict:
         """bench.py's N > 1 path: strong scaling of one R x k encode+commit over `world` GPUs."""
         mode = os.environ.get("LG_MGPU_MODE", "fused")
+        pipeline = {"0": False, "1": True}.get(os.environ.get("LG_MGPU_PIPELINE", ""), None)
         m = R // 4
-        sc = ShardedCommitter(ctx, m, k, rho, rank, world, mode)
+        sc = ShardedCommitter(ctx, m, k, rho, rank, world, mode, pipeline)
         dev = torch.device("cuda", ctx.device)
         g = torch.Generator(device=dev)
         g.manual_seed(20240 + rank)

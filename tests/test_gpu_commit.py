@@ -138,3 +138,49 @@ def test_invalid_arguments(gpu_ctx):
         gpu_ctx.commit(flat, 0, 2, 8)      # no rows
     with pytest.raises(LigeroB200Error):
         gpu_ctx.commit(flat, 1, 2, 3)      # rho_inv not a power of two
+
+
+@pytest.mark.parametrize("R,k,rho,cuts", [
+    (7, 8, 8, [3, 4]),            # odd and even boundaries, single-row tiles
+    (12, 64, 8, [1, 2, 5, 11]),
+    (9, 128, 4, [4, 5]),
+    (16, 2048, 8, [7]),
+    (5, 16, 8, [2]),
+])
+def test_tile_wise_column_hashing_matches_oracle(gpu_ctx, R, k, rho, cuts):
+    """lg_matrix_hash_rows / lg_matrix_hash_finish: a column's BLAKE2s stream carried across row tiles with
+    arbitrary (odd or even) boundaries gives the leaves and root of the one-shot hash and of the oracle."""
+    rnd = random.Random(R * 31 + k)
+    msg = rand_matrix(rnd, R, k, (1,) if R > 2 else ())
+    _, leaves, tree = oracle_encode_commit(msg, k, rho)
+    flat = fr_to_limbs([x for row in msg for x in row])
+    cm = gpu_ctx.encode(flat, R, k, rho)
+    try:
+        bounds = [0] + list(cuts) + [R]
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            cm.hash_rows(a, b)
+        root = cm.hash_finish()
+        assert root == tree.root()
+        got_leaves = cm.read_leaves()
+        assert [bytes(x) for x in got_leaves] == leaves
+        assert cm.hash() == tree.root()      # the one-shot path on the same matrix
+    finally:
+        cm.free()
+
+
+@pytest.mark.parametrize("prefix", [(1, 1), (0, 0)])
+def test_tile_wise_hashing_without_length_prefixes(gpu_ctx, prefix):
+    """the format switches change the block alignment: tiles must still agree with one shot."""
+    gpu_ctx.set_formats(*prefix)
+    try:
+        rnd = random.Random(99)
+        R, k, rho = 11, 32, 8
+        flat = fr_to_limbs([rnd.randrange(P) for _ in range(R * k)])
+        cm = gpu_ctx.encode(flat, R, k, rho)
+        one = cm.hash()
+        for a, b in ((0, 3), (3, 4), (4, 10), (10, 11)):
+            cm.hash_rows(a, b)
+        assert cm.hash_finish() == one
+        cm.free()
+    finally:
+        gpu_ctx.set_formats(1, 1)
