@@ -213,9 +213,25 @@ def main():
 
     if world > 1:
         from ligero_b200.parallel import ShardedCommitter
+        sampler = ClockSampler(local_rank)
+        sampler.start()
         result = ShardedCommitter.bench(ctx, R, k, RHO_INV, args, rank, world)
+        clocks = sampler.stop()
         if rank == 0:
             result["config"]["workload"] = workload_name(args.log_gates, R, k, n)
+            result["clocks"] = clocks
+            # dominant kernel on one rank: the shared-memory NTT over this rank's rows (same definition as N = 1)
+            kms = result.get("kernel_ms_per_launch_rank0", {})
+            rows_g = result.get("rows_per_rank", R // world)
+            blocks = 4 if result.get("hash_pipeline") else 1     # the block pipeline launches it once per row block
+            if kms.get("ntt_local"):
+                gbs = 32.0 * (rows_g / blocks) * k * RHO_INV / (kms["ntt_local"] * 1e-3) / 1e9
+                hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+                result["roofline"] = {
+                    "bound": "hbm", "kernel": "ntt_local_kernel (rank 0)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                    "note": "integer-issue bound, not HBM bound: see the N=1 line's int_roofline"}
+            result["cpu_baseline"] = None     # timed at N = 1 only
             print(json.dumps(result))
         dist.barrier()
         dist.destroy_process_group()

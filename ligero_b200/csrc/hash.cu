@@ -27,15 +27,22 @@ __device__ __forceinline__ Fr ld_fr_g(const Fr* p) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
+// The xor + rotate pairs (LOP3, SHF) can only run on the half-rate ALU pipe, which bounds the kernel; the
+// additions are therefore written as multiply-adds by 1 so that they issue on the FMA pipe (IMAD) instead of
+// taking ALU slots as IADD3 (ptxas otherwise splits them about evenly between the two pipes).
+// The multiplier is read from memory at run time: a literal 1 is folded back into IADD3 by ptxas.
+__device__ uint32_t g_b2s_one = 1;
+#define add_fma(a, b) ((a) * b2s_one + (b))
+
 #define B2S_G(a, b, c, d, x, y)        \
   do {                                 \
-    a = a + b + (x);                   \
+    a = add_fma(add_fma(a, b), (x));   \
     d = rotr32(d ^ a, 16);             \
-    c = c + d;                         \
+    c = add_fma(c, d);                 \
     b = rotr32(b ^ c, 12);             \
-    a = a + b + (y);                   \
+    a = add_fma(add_fma(a, b), (y));   \
     d = rotr32(d ^ a, 8);              \
-    c = c + d;                         \
+    c = add_fma(c, d);                 \
     b = rotr32(b ^ c, 7);              \
   } while (0)
 
@@ -51,7 +58,8 @@ __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnels
     B2S_G(v3, v4, v9, v14, m[s14], m[s15]);                                              \
   } while (0)
 
-__device__ __forceinline__ void blake2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint64_t t, bool last) {
+__device__ __forceinline__ void blake2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint64_t t, bool last,
+                                                 const uint32_t b2s_one) {
   uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
   uint32_t v8 = 0x6A09E667u, v9 = 0xBB67AE85u, v10 = 0x3C6EF372u, v11 = 0xA54FF53Au;
   uint32_t v12 = 0x510E527Fu ^ (uint32_t)t, v13 = 0x9B05688Cu ^ (uint32_t)(t >> 32);
@@ -92,6 +100,7 @@ __device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride,
                                                    uint32_t& c1, Fr& pend) {
   const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
   const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
+  const uint32_t b2s_one = g_b2s_one;
   Fr n0 = fr_zero(), n1 = fr_zero();
   if (have_pend) n0 = pend;
   else if (2 * b0 < row_lim) n0 = ld_fr_g(col + 2 * b0 * stride);
@@ -127,7 +136,7 @@ __device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride,
     }
     const bool last = (b + 1 == nblocks);
     const uint64_t t = last ? total : 64 * (b + 1);
-    blake2s_compress(h, m, t, last);
+    blake2s_compress(h, m, t, last, b2s_one);
   }
   pend = n0;  // row 2*b1 if the tile ends on it (odd row_lim), else unused
 }

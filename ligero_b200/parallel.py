@@ -279,8 +279,12 @@ class ShardedCommitter:
         assert sc.root() == root0
         ms_per_step = float(ms.item()) / args.steps
         marks = []
-        sc.commit_async(msg, marks)     # one extra, untimed step with per-phase events
+        ctx.set_timing(True)
+        ctx.phase_ms()
+        sc.commit_async(msg, marks)     # one extra, untimed step with per-phase and per-kernel events
         torch.cuda.synchronize()
+        kernel_ms = {p: v[0] / max(1, v[1]) for p, v in ctx.phase_ms().items() if v[1]}
+        ctx.set_timing(False)
         phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         value = R * k / (ms_per_step * 1e-3)
         # end to end: pinned host shard -> device, root back on the host, every step
@@ -311,6 +315,8 @@ class ShardedCommitter:
                     "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_ms,
                     "api": "ShardedCommitter.commit(host pinned row shard) -> root on host, per rank"},
             "gpu_launches": int(launches), "root": root0.hex(), "phase_ms_rank0": phase_ms,
+            "kernel_ms_per_launch_rank0": kernel_ms, "rows_per_rank": sc.rows_g,
+            "hash_pipeline": bool(sc.pipeline),
         }
 
 
