@@ -108,15 +108,14 @@ int lg_ipc_close(lg_ctx* ctx, void* ptr);
  *   cosets_scratch : device Fr[(rho_inv-1)*4*m_g*k], needed when k > 1024 (may be NULL otherwise)
  * Stream-ordered; the caller synchronises all ranks (e.g. an NCCL all-reduce on the context stream)
  * before hashing the shards. */
+/*   plain          : 1 = the shards belong to a COMMITTED matrix (plain integers inside);
+ *                    0 = keep the Montgomery form (e.g. the rows of r_a extended to the 2k domain for the linear test) */
 int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t k, uint32_t rho_inv, void* const* shard_u,
-                      int world, size_t m, size_t i0, uint64_t* cosets_scratch);
-
-/* device addresses of the resident arrays (stream-ordered interop with the caller's own kernels /
- * collectives): U in the plane layout, n*32 leaf bytes, (n-1)*32 node bytes (node 0 = root) */
+                      int world, size_t m, size_t i0, uint64_t* cosets_scratch, int plain);
 /* The same, for `nrows` local rows that are the CONSECUTIVE global rows [row_base, row_base + nrows) of the
  * rows_total-row matrix: lets a rank encode its share block by block (X, then Y, Z, W). */
 int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, size_t row_base, size_t rows_total, size_t k,
-                           uint32_t rho_inv, void* const* shard_u, int world, uint64_t* cosets_scratch);
+                           uint32_t rho_inv, void* const* shard_u, int world, uint64_t* cosets_scratch, int plain);
 /* Column hashing in row tiles (src/ligero/mod.rs:536-542, one BLAKE2s stream per column): hash rows
  * [row0, row_end) of every column on the context's second stream, ordered after everything enqueued on the
  * context stream so far; tiles must come in row order and cover [0, rows).  lg_matrix_hash_finish builds the
@@ -124,6 +123,9 @@ int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, 
  * Lets the hashing of the rows that have arrived overlap the encoding (and NVLink delivery) of the rest. */
 int lg_matrix_hash_rows(lg_matrix* m, size_t row0, size_t row_end);
 int lg_matrix_hash_finish(lg_matrix* m, uint8_t root_out[32]);
+
+/* device addresses of the resident arrays (stream-ordered interop with the caller's own kernels /
+ * collectives): U in the plane layout, n*32 leaf bytes, (n-1)*32 node bytes (node 0 = root) */
 void* lg_matrix_u_dev(const lg_matrix* m);
 void* lg_matrix_leaves_dev(const lg_matrix* m);
 void* lg_matrix_nodes_dev(const lg_matrix* m);
@@ -169,6 +171,20 @@ int lg_linear_test_seeded(lg_matrix* m, const lg_constraints* a, const uint8_t s
 /* ---- Test-Quadratic-Constraints polynomial: src/ligero/mod.rs:839-848 -------------------------- */
 /* q = sum_{i<m} r[i] (p_x,i p_y,i - p_z,i);  r_quad: Fr[m] */
 int lg_quadratic_test(lg_matrix* m, const uint64_t* r_quad, uint64_t* coeffs_out, size_t* len_out);
+
+/* The two tests in pieces, for a matrix that holds only a RANGE of columns (one rank of a column-sharded
+ * commitment): every rank evaluates q on the 2k-domain points of its own columns
+ * (index 2c + half, natural order), the slices are concatenated in rank order, and one inverse NTT of size 2k
+ * gives the coefficients with trailing zeros trimmed (src/ligero/mod.rs:723-736, 842-848).
+ *   lg_linear_ra      : r_a = r_linear^T A from the 32-byte seed, into a DEVICE buffer of 4mk elements (719-722)
+ *   lg_linear_evals   : r_even = this rank's columns of the rows of r_a, r_odd = the same rows extended to the odd
+ *                       points of the 2k domain (both DEVICE, rows x k of this matrix, Montgomery) -> 2k' values
+ *   lg_quadratic_evals: r_quad (m elements, host or device) -> 2k' values
+ *   lg_poly_from_evals: `size` = 2k values in natural order (host or device) -> coefficients, *len_out <= size */
+int lg_linear_ra(lg_ctx* ctx, const lg_constraints* a, const uint8_t seed[32], uint64_t* r_a_dev);
+int lg_linear_evals(lg_matrix* m, const uint64_t* r_even_dev, const uint64_t* r_odd_dev, uint64_t* evals_out);
+int lg_quadratic_evals(lg_matrix* m, const uint64_t* r_quad, uint64_t* evals_out);
+int lg_poly_from_evals(lg_ctx* ctx, const uint64_t* evals, size_t size, uint64_t* coeffs_out, size_t* len_out);
 
 /* ---- openings: src/ligero/mod.rs:935-955 (DenseMatrix::column + MerkleTree::generate_proof) ---- */
 /* cols_out: Fr[t*rows] (column q = U[:, idx[q]]);  sib_out: t*32 bytes (leaf_sibling_hash);
@@ -237,6 +253,15 @@ int lg_prove_matrix(lg_ligero* l, const uint64_t* preenc_u, lg_sponge* sponge, l
 /* verify, 613-644: *accepted = 1 iff every check passes (0 otherwise; errors only for resource failures) */
 int lg_verify(lg_ligero* l, const lg_proof* proof, lg_sponge* sponge, int* accepted);
 int lg_proof_free(lg_proof* p);
+/* borrowed handle of the circuit's constraint matrix A on the device (owned by the lg_ligero) */
+int lg_ligero_constraints(const lg_ligero* l, const lg_constraints** out);
+/* A proof from its parts (LigeroProof, src/ligero/mod.rs:96-144), for provers that run the transcript
+ * themselves (the multi-GPU prover): three openings in the order interleaved, linear, quadratic; each has t
+ * columns of `rows` elements, t leaf indices, t sibling digests and t x depth path digests (root side first). */
+int lg_proof_assemble(const uint8_t root[32], const uint64_t* preenc_u_lc, size_t k, const uint64_t* linear_poly,
+                      size_t linear_len, const uint64_t* quadratic_poly, size_t quadratic_len, size_t t, size_t rows,
+                      size_t depth, const uint64_t* const cols[3], const uint64_t* const idx[3],
+                      const uint8_t* const sib[3], const uint8_t* const auth[3], lg_proof** out);
 /* Proof wire format (the reference defines none: LigeroProof has no derives, mod.rs:96-144): the layout
  * arkworks' CanonicalSerialize would give the same structs -- little endian, Vec<T> = u64 length + items,
  * Fr = 32 canonical bytes, digests = Vec<u8>, Path = {leaf_sibling_hash, auth_path, leaf_index: u64}:

@@ -46,9 +46,17 @@ SIGNATURES = {
     "lg_ipc_open": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "lg_ipc_close": (c_int, [c_void_p, c_void_p]),
     "lg_encode_sharded": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, POINTER(c_void_p), c_int, c_size_t,
-                                  c_size_t, c_void_p]),
+                                  c_size_t, c_void_p, c_int]),
     "lg_encode_sharded_rows": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_size_t, c_uint32,
-                                       POINTER(c_void_p), c_int, c_void_p]),
+                                       POINTER(c_void_p), c_int, c_void_p, c_int]),
+    "lg_linear_ra": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lg_linear_evals": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lg_quadratic_evals": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lg_poly_from_evals": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
+    "lg_ligero_constraints": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "lg_proof_assemble": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t,
+                                  c_size_t, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                  POINTER(c_void_p)]),
     "lg_matrix_hash_rows": (c_int, [c_void_p, c_size_t, c_size_t]),
     "lg_matrix_hash_finish": (c_int, [c_void_p, c_void_p]),
     "lg_matrix_u_dev": (c_void_p, [c_void_p]),

@@ -211,6 +211,11 @@ class PoseidonSponge:
         a = fr_to_limbs(elems)
         check(self.lib.lg_sponge_absorb_fr(self.handle, _ptr(a) if len(a) else None, len(a)), None, "absorb")
 
+    def absorb_fr(self, limbs):
+        """absorb(&Vec<F>) from Montgomery-form limbs (uint64[count, 4]) as they come back from the device"""
+        a = np.ascontiguousarray(limbs, dtype=np.uint64).reshape(-1, 4)
+        check(self.lib.lg_sponge_absorb_fr(self.handle, _ptr(a) if len(a) else None, len(a)), None, "absorb")
+
     def squeeze_bytes(self, n: int) -> bytes:
         out = np.zeros(n, dtype=np.uint8)
         check(self.lib.lg_sponge_squeeze_bytes(self.handle, _ptr(out), n), None, "squeeze")

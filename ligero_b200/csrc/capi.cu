@@ -586,7 +586,7 @@ int lg_ipc_close(lg_ctx* ctx, void* ptr) {
 }
 
 int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t k, uint32_t rho_inv, void* const* shard_u,
-                      int world, size_t m, size_t i0, uint64_t* cosets_scratch) {
+                      int world, size_t m, size_t i0, uint64_t* cosets_scratch, int plain) {
   if (!ctx || !shard_u) return ERR_INVALID;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
@@ -613,7 +613,7 @@ int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(ctx, msg_local, rows * k, &dev, &to_free));
-  int s = encode_rows(c, dev, rows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map, true);
+  int s = encode_rows(c, dev, rows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map, plain != 0);
   if (to_free) {
     cudaStreamSynchronize(c->stream);
     cudaFree(to_free);
@@ -622,7 +622,7 @@ int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t
 }
 
 int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, size_t row_base, size_t rows_total, size_t k,
-                           uint32_t rho_inv, void* const* shard_u, int world, uint64_t* cosets_scratch) {
+                           uint32_t rho_inv, void* const* shard_u, int world, uint64_t* cosets_scratch, int plain) {
   if (!ctx || !shard_u) return ERR_INVALID;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
@@ -647,7 +647,7 @@ int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, 
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(ctx, msg_rows, nrows * k, &dev, &to_free));
-  int s = encode_rows(c, dev, nrows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map, true);
+  int s = encode_rows(c, dev, nrows, log_k, (int)rho_inv, nullptr, (Fr*)cosets_scratch, &map, plain != 0);
   if (to_free) {
     cudaStreamSynchronize(c->stream);
     cudaFree(to_free);

@@ -1071,6 +1071,50 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
 // ---------------------------------------------------------------------------------------------------
 // proof container
 // ---------------------------------------------------------------------------------------------------
+int lg_ligero_constraints(const lg_ligero* L, const lg_constraints** out) {
+  if (!L || !out) return ERR_INVALID;
+  *out = L->a;
+  return OK;
+}
+
+int lg_proof_assemble(const uint8_t root[32], const uint64_t* preenc_u_lc, size_t k, const uint64_t* linear_poly,
+                      size_t linear_len, const uint64_t* quadratic_poly, size_t quadratic_len, size_t t, size_t rows,
+                      size_t depth, const uint64_t* const cols[3], const uint64_t* const idx[3],
+                      const uint8_t* const sib[3], const uint8_t* const auth[3], lg_proof** out) {
+  if (!root || !out || (k && !preenc_u_lc) || (linear_len && !linear_poly) || (quadratic_len && !quadratic_poly) || !cols ||
+      !idx || !sib || !auth)
+    return ERR_INVALID;
+  lg_proof* P = new (std::nothrow) lg_proof();
+  if (!P) return ERR_NOMEM;
+  memcpy(P->root.data(), root, 32);
+  P->preenc_u_lc.resize(k);
+  if (k) memcpy(P->preenc_u_lc.data(), preenc_u_lc, k * 32);
+  P->linear_poly.resize(linear_len);
+  if (linear_len) memcpy(P->linear_poly.data(), linear_poly, linear_len * 32);
+  P->quadratic_poly.resize(quadratic_len);
+  if (quadratic_len) memcpy(P->quadratic_poly.data(), quadratic_poly, quadratic_len * 32);
+  Opened* parts[3] = {&P->interleaved, &P->linear, &P->quadratic};
+  for (int p = 0; p < 3; p++) {
+    if (t && (!cols[p] || !idx[p] || !sib[p] || (depth && !auth[p]))) {
+      delete P;
+      return ERR_INVALID;
+    }
+    Opened& o = *parts[p];
+    o.columns.resize(t);
+    o.leaf_index.assign(idx[p], idx[p] + t);
+    o.sibling.resize(t);
+    o.auth.assign(t, std::vector<Digest>(depth));
+    for (size_t q = 0; q < t; q++) {
+      o.columns[q].resize(rows);
+      memcpy(o.columns[q].data(), cols[p] + 4 * q * rows, rows * 32);
+      memcpy(o.sibling[q].data(), sib[p] + 32 * q, 32);
+      for (size_t d = 0; d < depth; d++) memcpy(o.auth[q][d].data(), auth[p] + 32 * (q * depth + d), 32);
+    }
+  }
+  *out = P;
+  return OK;
+}
+
 int lg_proof_free(lg_proof* p) {
   delete p;
   return OK;

@@ -184,6 +184,32 @@ int lg_sparse_row_mul(lg_ctx* ctx, const lg_constraints* a, const uint64_t* r_li
   return OK;
 }
 
+// q on the 2k domain restricted to this matrix's columns (natural order: index 2c + half), on the device:
+//   q(zeta^(2c))   = sum_i r_even[i][c] U[i][rho c]             (plane 0)
+//   q(zeta^(2c+1)) = sum_i r_odd[i][c]  U[i][rho c + rho/2]     (plane rho/2)
+static int linear_evals_dev(Matrix& m, const Fr* r_even, const Fr* r_odd, Fr* qhat) {
+  Ctx* c = m.ctx;
+  const size_t plane = m.rows * m.k;
+  phase_mark(c, PH_BEGIN);
+  // the planes of the committed matrix hold plain integers (x_plain)
+  LG_TRY(col_reduce(c, 1, r_even, m.u, nullptr, nullptr, m.rows, m.k, qhat, 2, 0, true));
+  LG_TRY(col_reduce(c, 1, r_odd, m.u + (size_t)(m.rho_inv / 2) * plane, nullptr, nullptr, m.rows, m.k, qhat, 2, 1, true));
+  phase_mark(c, PH_TESTS);
+  return OK;
+}
+
+static int quadratic_evals_dev(Matrix& m, const Fr* r_quad, Fr* qhat) {
+  Ctx* c = m.ctx;
+  const size_t mm = m.rows / 4, plane = m.rows * m.k;
+  phase_mark(c, PH_BEGIN);
+  for (int half = 0; half < 2; half++) {
+    const Fr* p = m.u + (size_t)(half ? m.rho_inv / 2 : 0) * plane;
+    LG_TRY(col_reduce(c, 2, r_quad, p, p + mm * m.k, p + 2 * mm * m.k, mm, m.k, qhat, 2, half, true));
+  }
+  phase_mark(c, PH_TESTS);
+  return OK;
+}
+
 // shared tail of the linear test once r_a is on the device (and may be clobbered)
 static int linear_test_core(lg_matrix* h, Fr* r_a, uint64_t* coeffs_out, size_t* len_out) {
   Matrix& m = h->m;
@@ -194,12 +220,7 @@ static int linear_test_core(lg_matrix* h, Fr* r_a, uint64_t* coeffs_out, size_t*
   LG_TRY(odd.alloc(c, plane * sizeof(Fr)));
   LG_TRY(qhat.alloc(c, 2 * m.k * sizeof(Fr)));
   LG_TRY(encode_rows(c, r_a, m.rows, m.log_k, 2, nullptr, (Fr*)odd.p));
-  phase_mark(c, PH_BEGIN);
-  // q(zeta^(2c)) = sum_i r_a[i][c] U[i][rho c];   q(zeta^(2c+1)) = sum_i r_odd[i][c] U[i][rho c + rho/2]
-  LG_TRY(col_reduce(c, 1, r_a, m.u, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 0, true));
-  LG_TRY(col_reduce(c, 1, (const Fr*)odd.p, m.u + (size_t)(m.rho_inv / 2) * plane, nullptr, nullptr, m.rows, m.k, (Fr*)qhat.p, 2, 1,
-                    true));  // the planes of the committed matrix hold plain integers
-  phase_mark(c, PH_TESTS);
+  LG_TRY(linear_evals_dev(m, r_a, (const Fr*)odd.p, (Fr*)qhat.p));
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);
 }
 
@@ -243,13 +264,62 @@ int lg_quadratic_test(lg_matrix* h, const uint64_t* r_quad, uint64_t* coeffs_out
   LG_TRY(rin.init(c, r_quad, mm * sizeof(Fr)));
   DevBuf qhat;
   LG_TRY(qhat.alloc(c, 2 * m.k * sizeof(Fr)));
-  phase_mark(c, PH_BEGIN);
-  for (int half = 0; half < 2; half++) {
-    const Fr* p = m.u + (size_t)(half ? m.rho_inv / 2 : 0) * plane;
-    LG_TRY(col_reduce(c, 2, (const Fr*)rin.ptr, p, p + mm * m.k, p + 2 * mm * m.k, mm, m.k, (Fr*)qhat.p, 2, half, true));
-  }
-  phase_mark(c, PH_TESTS);
+  LG_TRY(quadratic_evals_dev(m, (const Fr*)rin.ptr, (Fr*)qhat.p));
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);
+}
+
+// ---- the same tests in pieces, for a column-sharded matrix (one rank's columns) -----------
+int lg_linear_ra(lg_ctx* ctx, const lg_constraints* a, const uint8_t seed[32], uint64_t* r_a_dev) {
+  if (!ctx || !a || !seed || !r_a_dev) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (!is_device_ptr(r_a_dev)) return set_error(c, ERR_INVALID, "lg_linear_ra writes a device buffer of 4mk elements");
+  LG_TRY(expand_fr(c, seed, 4 * a->mk, (Fr*)r_a_dev));  // get_field_elements_from_prng(4mk) on the device
+  return compute_r_a_inplace(c, a, (Fr*)r_a_dev);
+}
+
+int lg_linear_evals(lg_matrix* h, const uint64_t* r_even_dev, const uint64_t* r_odd_dev, uint64_t* evals_out) {
+  if (!h || !r_even_dev || !r_odd_dev || !evals_out) return ERR_INVALID;
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  cudaSetDevice(c->device);
+  if (m.rho_inv < 2) return set_error(c, ERR_UNSUPPORTED, "the tests need the 2k domain inside the codeword (rho_inv >= 2)");
+  if (!is_device_ptr(r_even_dev) || !is_device_ptr(r_odd_dev)) return set_error(c, ERR_INVALID, "r matrices must be device buffers");
+  DevBuf qhat;
+  LG_TRY(qhat.alloc(c, 2 * m.k * sizeof(Fr)));
+  LG_TRY(linear_evals_dev(m, (const Fr*)r_even_dev, (const Fr*)r_odd_dev, (Fr*)qhat.p));
+  LG_CUDA(c, cudaMemcpyAsync(evals_out, qhat.p, 2 * m.k * sizeof(Fr), cudaMemcpyDefault, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OK;
+}
+
+int lg_quadratic_evals(lg_matrix* h, const uint64_t* r_quad, uint64_t* evals_out) {
+  if (!h || !r_quad || !evals_out) return ERR_INVALID;
+  Matrix& m = h->m;
+  Ctx* c = m.ctx;
+  cudaSetDevice(c->device);
+  if (m.rows % 4) return set_error(c, ERR_INVALID, "rows must be 4m");
+  if (m.rho_inv < 2) return set_error(c, ERR_UNSUPPORTED, "the tests need the 2k domain inside the codeword (rho_inv >= 2)");
+  DevIn rin;
+  LG_TRY(rin.init(c, r_quad, (m.rows / 4) * sizeof(Fr)));
+  DevBuf qhat;
+  LG_TRY(qhat.alloc(c, 2 * m.k * sizeof(Fr)));
+  LG_TRY(quadratic_evals_dev(m, (const Fr*)rin.ptr, (Fr*)qhat.p));
+  LG_CUDA(c, cudaMemcpyAsync(evals_out, qhat.p, 2 * m.k * sizeof(Fr), cudaMemcpyDefault, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return OK;
+}
+
+int lg_poly_from_evals(lg_ctx* ctx, const uint64_t* evals, size_t size, uint64_t* coeffs_out, size_t* len_out) {
+  if (!ctx || !evals || size < 4 || (size & (size - 1))) return ERR_INVALID;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  int log_k = 0;
+  while (((size_t)2 << log_k) < size) log_k++;
+  DevBuf q;
+  LG_TRY(q.alloc(c, size * sizeof(Fr)));
+  LG_CUDA(c, cudaMemcpyAsync(q.p, evals, size * sizeof(Fr), cudaMemcpyDefault, c->stream));
+  return finish_poly(c, (Fr*)q.p, log_k, coeffs_out, len_out);
 }
 
 int lg_open(lg_matrix* h, const uint64_t* idx, size_t t, uint64_t* cols_out, uint8_t* sib_out, uint8_t* auth_out) {

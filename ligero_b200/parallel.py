@@ -73,6 +73,40 @@ def combine_subtree_roots(roots: Sequence[bytes]) -> bytes:
     return level[0]
 
 
+def top_auth_paths(roots: Sequence[bytes]) -> List[List[bytes]]:
+    """For each of the G subtrees: the sibling digests on the way from its root to the tree root, listed from
+    just below the root downwards (the order of ark_crypto_primitives::Path::auth_path, SURVEY A.5)."""
+    g = len(roots)
+    assert g & (g - 1) == 0
+    levels = [list(roots)]
+    while len(levels[-1]) > 1:
+        lv = levels[-1]
+        levels.append([hashlib.sha256(lv[2 * i] + lv[2 * i + 1]).digest() for i in range(len(lv) // 2)])
+    paths = []
+    for h in range(g):
+        sib, pos = [], h
+        for lv in levels[:-1]:           # bottom (subtree roots) upwards
+            sib.append(lv[pos ^ 1])
+            pos >>= 1
+        paths.append(sib[::-1])          # root side first
+    return paths
+
+
+def split_openings(idx: Sequence[int], n: int, world: int) -> List[Tuple[int, int]]:
+    """(owner rank, leaf index inside the owner's subtree) of every opened column: rank h owns the contiguous
+    leaves [h*n/G, (h+1)*n/G) (= message indices [h*k/G, (h+1)*k/G) in all coset planes)."""
+    per = n // world
+    return [(int(j) // per, int(j) % per) for j in idx]
+
+
+def gather_concat(part: torch.Tensor) -> torch.Tensor:
+    """concatenation over ranks (rank order) of equally shaped tensors: the all-gather of column slices"""
+    world = dist.get_world_size()
+    outs = [torch.empty_like(part) for _ in range(world)]
+    dist.all_gather(outs, part.contiguous())
+    return torch.cat(outs, dim=0)
+
+
 def exchange(send: List[torch.Tensor], recv: List[torch.Tensor]) -> None:
     """all-to-all of per-destination blocks.  NCCL: one grouped all_to_all over NVLink; gloo (CPU tests):
     emulated with broadcasts, because gloo has no all_to_all."""
@@ -95,6 +129,32 @@ def exchange(send: List[torch.Tensor], recv: List[torch.Tensor]) -> None:
 # --------------------------------------------------------------------------------------------
 # device path
 # --------------------------------------------------------------------------------------------
+def open_peer_shards(ctx, rows: int, kg: int, rho: int, rank: int, world: int):
+    """One column-shard matrix (rows x kg, rho planes) per rank, each mapped into every peer with CUDA IPC.
+    Returns (this rank's CommittedMatrix, ctypes array of the `world` shard base pointers, peer pointers to close)."""
+    from ctypes import byref, c_void_p
+    import numpy as np
+    from .backend import CommittedMatrix, check
+    h = c_void_p()
+    check(ctx.lib.lg_matrix_create(ctx.handle, rows, kg, rho, byref(h)), ctx.handle, "lg_matrix_create")
+    mat = CommittedMatrix(ctx, h, None)
+    handle = np.zeros(64, dtype=np.uint8)
+    check(ctx.lib.lg_ipc_export(mat.handle, handle.ctypes.data), ctx.handle, "lg_ipc_export")
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(handle))
+    ptrs, peers = [], []
+    for g in range(world):
+        if g == rank:
+            ptrs.append(int(ctx.lib.lg_matrix_u_dev(mat.handle)))
+        else:
+            p = c_void_p()
+            hb = np.frombuffer(handles[g], dtype=np.uint8).copy()
+            check(ctx.lib.lg_ipc_open(ctx.handle, hb.ctypes.data, byref(p)), ctx.handle, "lg_ipc_open")
+            ptrs.append(int(p.value))
+            peers.append(int(p.value))
+    return mat, (c_void_p * world)(*ptrs), peers
+
+
 class ShardedCommitter:
     """Row-sharded encode -> exchange -> column-sharded hash + subtree -> root all-gather.
 
@@ -139,27 +199,7 @@ class ShardedCommitter:
             self.mat_rows = ctx.wrap(self.u_rows, max(self.rows_g, 1), k, rho) if self.rows_g else None
             self.mat_cols = ctx.wrap(self.u_cols, 4 * m, self.kg, rho)
         else:
-            from ctypes import byref, c_void_p
-            import numpy as np
-            from .backend import CommittedMatrix, check
-            h = c_void_p()
-            check(ctx.lib.lg_matrix_create(ctx.handle, 4 * m, self.kg, rho, byref(h)), ctx.handle, "lg_matrix_create")
-            self.mat_cols = CommittedMatrix(ctx, h, None)
-            handle = np.zeros(64, dtype=np.uint8)
-            check(ctx.lib.lg_ipc_export(self.mat_cols.handle, handle.ctypes.data), ctx.handle, "lg_ipc_export")
-            handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle))
-            ptrs = []
-            for g in range(world):
-                if g == rank:
-                    ptrs.append(int(ctx.lib.lg_matrix_u_dev(self.mat_cols.handle)))
-                else:
-                    p = c_void_p()
-                    hb = np.frombuffer(handles[g], dtype=np.uint8).copy()
-                    check(ctx.lib.lg_ipc_open(ctx.handle, hb.ctypes.data, byref(p)), ctx.handle, "lg_ipc_open")
-                    ptrs.append(int(p.value))
-                    self._peer_ptrs.append(int(p.value))
-            self.shard_ptrs = (c_void_p * world)(*ptrs)
+            self.mat_cols, self.shard_ptrs, self._peer_ptrs = open_peer_shards(ctx, 4 * m, self.kg, rho, rank, world)
             # local intermediate of the coset planes, only for rows longer than one CTA tile (k > 1024)
             self.scratch = (torch.empty(((rho - 1) * max(self.rows_g, 1) * k, 4), dtype=torch.int64, device=dev)
                             if k > 1024 else None)
@@ -205,7 +245,7 @@ class ShardedCommitter:
                     off = b * self.m_g * self.k * 32
                     check(lib.lg_encode_sharded_rows(self.ctx.handle, base + off if self.m_g else None, self.m_g,
                                                      b * self.m + self.i0, 4 * self.m, self.k, self.rho,
-                                                     self.shard_ptrs, self.world, scratch),
+                                                     self.shard_ptrs, self.world, scratch, 1),
                           self.ctx.handle, "lg_encode_sharded_rows")
                     dist.all_reduce(self.flag)      # block b has landed on every rank ...
                     check(lib.lg_matrix_hash_rows(self.mat_cols.handle, b * self.m, (b + 1) * self.m),
@@ -216,7 +256,7 @@ class ShardedCommitter:
             else:
                 check(self.ctx.lib.lg_encode_sharded(self.ctx.handle, _ptr(msg_local), self.m_g, self.k, self.rho,
                                                      self.shard_ptrs, self.world, self.m, self.i0,
-                                                     _ptr(self.scratch) if self.scratch is not None else None),
+                                                     _ptr(self.scratch) if self.scratch is not None else None, 1),
                       self.ctx.handle, "lg_encode_sharded")
                 mark("encode+scatter over NVLink")
                 dist.all_reduce(self.flag)      # every rank's stores have landed before anyone hashes
@@ -318,6 +358,155 @@ class ShardedCommitter:
             "kernel_ms_per_launch_rank0": kernel_ms, "rows_per_rank": sc.rows_g,
             "hash_pipeline": bool(sc.pipeline),
         }
+
+
+class ShardedProver:
+    """LigeroCircuit::prove over G GPUs (SURVEY 8e): the commitment is ShardedCommitter's; afterwards every rank
+    holds ALL rows of its column range, so the three tests are column-parallel with no partial sums to reduce:
+
+      Test-Interleaved   r^T U_pre on the rank's columns                      -> all-gather of k/G values
+      Test-Linear        r_a = r^T A (replicated, O(nnz)); its 4m rows are extended to the odd points of the 2k
+                         domain row-sharded, with the same fused NVLink scatter as the witness (rho = 2, Montgomery
+                         form kept); q on the rank's 2k/G points               -> all-gather, one inverse NTT
+      Test-Quadratic     q on the rank's 2k/G points                           -> all-gather, one inverse NTT
+      openings           the owner of a column returns it with the path inside its subtree; the top log2(G)
+                         siblings come from the all-gathered subtree roots
+
+    Every rank runs the same Fiat-Shamir transcript on the gathered values, so all ranks end with the same proof,
+    byte-identical to the single-GPU (and the reference's) proof for the same witness and sponge."""
+
+    def __init__(self, ctx, ligero, rank: int, world: int):
+        from ctypes import byref, c_void_p
+        from .backend import check
+        self.ctx, self.L, self.rank, self.world = ctx, ligero, rank, world
+        self.m, self.k, self.n, self.t = ligero.m, ligero.k, ligero.n, ligero.t
+        self.rho = self.n // self.k
+        self.committer = ShardedCommitter(ctx, self.m, self.k, self.rho, rank, world, "fused")
+        c = self.committer
+        self.rows, self.kg = 4 * self.m, c.kg
+        self.rhat, self.rhat_ptrs, self._rhat_peers = open_peer_shards(ctx, self.rows, self.kg, 2, rank, world)
+        self.rhat_scratch = (torch.empty((max(c.rows_g, 1) * self.k, 4), dtype=torch.int64, device=c.dev)
+                             if self.k > 1024 else None)
+        self.row_ids = torch.tensor(local_row_ids(self.m, world, rank), dtype=torch.int64, device=c.dev)
+        a = c_void_p()
+        check(ctx.lib.lg_ligero_constraints(ligero.handle, byref(a)), ctx.handle, "lg_ligero_constraints")
+        self.a = a
+        dist.barrier()
+
+    def close(self):
+        self.ctx.sync()
+        dist.barrier()
+        for p in self._rhat_peers:
+            self.ctx.lib.lg_ipc_close(self.ctx.handle, p)
+        self._rhat_peers = []
+        dist.barrier()
+        self.rhat.free()
+        self.committer.close()
+
+    def local_rows(self, preenc_u):
+        """this rank's rows [X_g; Y_g; Z_g; W_g] of a full 4m x k pre-encoding matrix (numpy or torch, [4mk, 4])"""
+        full = torch.as_tensor(preenc_u.view("int64") if hasattr(preenc_u, "ctypes") else preenc_u)
+        loc = full.view(self.rows, self.k, 4)[self.row_ids.to(full.device)].reshape(-1, 4).contiguous()
+        return loc.to(self.committer.dev)
+
+    # -- collectives over host-sized results -------------------------------------------------------
+    def _gather(self, part_np):
+        import numpy as np
+        t = torch.from_numpy(np.ascontiguousarray(part_np).view(np.int64)).to(self.committer.dev)
+        return gather_concat(t).cpu().numpy().view(np.uint64)
+
+    def _open(self, sponge, subtree_roots):
+        import numpy as np
+        dev, world, rank = self.committer.dev, self.world, self.rank
+        idx = self.ctx.expand_indices(sponge.squeeze_bytes(32), self.n, self.t)
+        where = split_openings(idx, self.n, world)
+        mine = [q for q, (h, _) in enumerate(where) if h == rank]
+        depth_local = (self.n // world).bit_length() - 2
+        cols_all = torch.zeros((self.t, self.rows, 4), dtype=torch.int64, device=dev)
+        sib_all = torch.zeros((self.t, 4), dtype=torch.int64, device=dev)
+        auth_all = torch.zeros((self.t, max(depth_local, 0) * 4 + 1), dtype=torch.int64, device=dev)
+        if mine:
+            cols, sib, auth = self.committer.mat_cols.open(np.array([where[q][1] for q in mine], dtype=np.uint64))
+            sel = torch.tensor(mine, dtype=torch.int64, device=dev)
+            cols_all[sel] = torch.from_numpy(cols.view(np.int64)).to(dev)
+            sib_all[sel] = torch.from_numpy(sib.view(np.int64).reshape(len(mine), 4)).to(dev)
+            if depth_local > 0:
+                auth_all[sel, : depth_local * 4] = torch.from_numpy(auth.view(np.int64).reshape(len(mine), depth_local * 4)).to(dev)
+        # exactly one rank contributes a non-zero row per opened column: the sum is a gather
+        for tns in (cols_all, sib_all, auth_all):
+            dist.all_reduce(tns)
+        top = top_auth_paths(subtree_roots)
+        cols_np = cols_all.cpu().numpy().view(np.uint64)
+        sib_np = sib_all.cpu().numpy().view(np.uint8).reshape(self.t, 32)
+        auth_loc = auth_all[:, : max(depth_local, 0) * 4].cpu().numpy().view(np.uint8).reshape(self.t, max(depth_local, 0), 32)
+        depth = self.n.bit_length() - 2
+        auth_np = np.zeros((self.t, depth, 32), dtype=np.uint8)
+        ntop = depth - max(depth_local, 0)
+        for q, (h, _) in enumerate(where):
+            for d in range(ntop):
+                auth_np[q, d] = np.frombuffer(top[h][d], dtype=np.uint8)
+            auth_np[q, ntop:] = auth_loc[q]
+        return cols_np, np.ascontiguousarray(idx, dtype=np.uint64), sib_np, auth_np
+
+    def prove_matrix(self, local_rows, sponge):
+        """local_rows: this rank's rows of the pre-encoding matrix (see local_rows()); returns a LigeroProof."""
+        import numpy as np
+        from ctypes import byref, c_size_t, c_void_p
+        from .api import LigeroProof
+        from .backend import _ptr, check
+        ctx, lib, c = self.ctx, self.ctx.lib, self.committer
+        root = c.commit(local_rows)                                            # mod.rs:521-551
+        r_host = c.roots.cpu().numpy()
+        subtree_roots = [bytes(r_host[g]) for g in range(self.world)]
+        sponge.absorb_bytes(root)                                              # 560
+        # Test-Interleaved (646-669)
+        r = ctx.expand_fr(sponge.squeeze_bytes(32), self.rows)
+        lc = self._gather(c.mat_cols.row_combine(r))                           # k x 4
+        sponge.absorb_fr(lc)
+        opened = [self._open(sponge, subtree_roots)]
+        # Test-Linear-Constraints (712-747)
+        seed = np.frombuffer(sponge.squeeze_bytes(32), dtype=np.uint8).copy()
+        r_a = torch.empty((self.rows * self.k, 4), dtype=torch.int64, device=c.dev)
+        check(lib.lg_linear_ra(ctx.handle, self.a, _ptr(seed), _ptr(r_a)), ctx.handle, "lg_linear_ra")
+        loc = r_a.view(self.rows, self.k, 4)[self.row_ids].reshape(-1, 4).contiguous() if c.m_g else None
+        with torch.cuda.stream(c.stream):
+            check(lib.lg_encode_sharded(ctx.handle, _ptr(loc) if loc is not None else None, c.m_g, self.k, 2, self.rhat_ptrs,
+                                        self.world, self.m, c.i0,
+                                        _ptr(self.rhat_scratch) if self.rhat_scratch is not None else None, 0),
+                  ctx.handle, "lg_encode_sharded(r_a)")
+            dist.all_reduce(c.flag)        # every rank's rows of r-hat have landed
+        ctx.sync()
+        base = int(lib.lg_matrix_u_dev(self.rhat.handle))
+        ev = np.empty((2 * self.kg, 4), dtype=np.uint64)
+        check(lib.lg_linear_evals(c.mat_cols.handle, c_void_p(base), c_void_p(base + self.rows * self.kg * 32), _ptr(ev)),
+              ctx.handle, "lg_linear_evals")
+        lin = self._poly(self._gather(ev))
+        sponge.absorb_fr(lin)
+        opened.append(self._open(sponge, subtree_roots))
+        # Test-Quadratic-Constraints (832-859)
+        rq = ctx.expand_fr(sponge.squeeze_bytes(32), self.m)
+        check(lib.lg_quadratic_evals(c.mat_cols.handle, _ptr(rq), _ptr(ev)), ctx.handle, "lg_quadratic_evals")
+        quad = self._poly(self._gather(ev))
+        sponge.absorb_fr(quad)
+        opened.append(self._open(sponge, subtree_roots))
+        # LigeroProof
+        depth = self.n.bit_length() - 2
+        arr = lambda j: (c_void_p * 3)(*[_ptr(o[j]).value for o in opened])
+        rootb = np.frombuffer(root, dtype=np.uint8).copy()
+        h = c_void_p()
+        check(lib.lg_proof_assemble(_ptr(rootb), _ptr(lc), self.k, _ptr(lin), len(lin), _ptr(quad), len(quad), self.t, self.rows,
+                                    depth, arr(0), arr(1), arr(2), arr(3), byref(h)), ctx.handle, "lg_proof_assemble")
+        return LigeroProof(h)
+
+    def _poly(self, evals_np):
+        import numpy as np
+        from ctypes import byref, c_size_t
+        from .backend import _ptr, check
+        out = np.empty((2 * self.k, 4), dtype=np.uint64)
+        n = c_size_t()
+        check(self.ctx.lib.lg_poly_from_evals(self.ctx.handle, _ptr(np.ascontiguousarray(evals_np)), 2 * self.k, _ptr(out), byref(n)),
+              self.ctx.handle, "lg_poly_from_evals")
+        return np.ascontiguousarray(out[: n.value])
 
 
 class _DevBytes:

@@ -97,3 +97,56 @@ def test_top_of_tree():
     l1 = hashlib.sha256(roots[2] + roots[3]).digest()
     assert par.combine_subtree_roots(roots) == hashlib.sha256(l0 + l1).digest()
     assert par.combine_subtree_roots(roots[:1]) == roots[0]
+
+
+# ---- host logic of the multi-GPU prover (ShardedProver): column ownership, path assembly, slice gathers ----------
+def test_sharded_openings_paths_match_unsharded_tree():
+    """Paths assembled from (path inside the owner's subtree) + (siblings over the gathered subtree roots) are the
+    oracle's MerkleTree paths of the whole tree, for every leaf."""
+    rnd = random.Random(5)
+    for world, n in ((2, 8), (4, 16), (8, 64), (2, 4), (4, 8)):
+        leaves = [bytes(rnd.randrange(256) for _ in range(32)) for _ in range(n)]
+        whole = O.MerkleTree(leaves)
+        per = n // world
+        subs = [O.MerkleTree(leaves[h * per:(h + 1) * per]) for h in range(world)]
+        top = par.top_auth_paths([s.root() for s in subs])
+        assert par.combine_subtree_roots([s.root() for s in subs]) == whole.root()
+        where = par.split_openings(list(range(n)), n, world)
+        for j in range(n):
+            h, jl = where[j]
+            assert (h, jl) == (j // per, j % per)
+            local = subs[h].generate_proof(jl)
+            want = whole.generate_proof(j)
+            assert local.leaf_sibling_hash == want.leaf_sibling_hash
+            assert top[h] + local.auth_path == want.auth_path
+
+
+def _gather_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        part = torch.arange(6, dtype=torch.int64).view(3, 2) + 100 * rank      # this rank's column slice
+        full = par.gather_concat(part)
+        want = torch.cat([torch.arange(6, dtype=torch.int64).view(3, 2) + 100 * r for r in range(world)])
+        # the "sum as gather" used for the opened columns: exactly one rank contributes each row
+        rows = torch.zeros((2 * world, 4), dtype=torch.int64)
+        rows[2 * rank: 2 * rank + 2] = torch.tensor([[-1, 2 ** 62, rank, 7]] * 2, dtype=torch.int64)
+        dist.all_reduce(rows)
+        ok_rows = all(int(rows[2 * r, 2]) == r and int(rows[2 * r, 0]) == -1 for r in range(world))
+        q.put((rank, bool(torch.equal(full, want)) and ok_rows))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_of_column_slices_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok in results), results
