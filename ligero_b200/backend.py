@@ -100,6 +100,10 @@ class Context:
         """Overlap column hashing with encoding inside commit/recommit (default on)."""
         check(self.lib.lg_ctx_set_overlap(self.handle, int(enabled)), self.handle)
 
+    def set_hash_quad_max(self, max_columns: int):
+        """Whole-matrix column hashes of at most `max_columns` columns use the four-lanes-per-column kernel (0: never)."""
+        check(self.lib.lg_ctx_set_hash_quad_max(self.handle, int(max_columns)), self.handle)
+
     def phase_ms(self):
         """{phase: (accumulated ms, intervals)} since the last call (synchronises the stream)."""
         n = len(self.PHASES)

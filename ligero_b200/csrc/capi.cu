@@ -387,6 +387,7 @@ int lg_ctx_create(int device, lg_ctx** out) {
   }
   cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device);
   if (const char* e = getenv("LG_OVERLAP")) ctx->c.overlap = atoi(e) != 0;  // tuning hook; see lg_ctx_set_overlap
+  if (const char* e = getenv("LG_HASH_QUAD_MAX")) ctx->c.hash_quad_max = (size_t)strtoull(e, nullptr, 10);
   *out = ctx;
   return OK;
 }
@@ -445,6 +446,12 @@ void* lg_ctx_stream(const lg_ctx* ctx) { return ctx ? (void*)ctx->c.stream : nul
 int lg_ctx_set_overlap(lg_ctx* ctx, int enabled) {
   if (!ctx) return ERR_INVALID;
   ctx->c.overlap = enabled != 0;
+  return OK;
+}
+
+int lg_ctx_set_hash_quad_max(lg_ctx* ctx, size_t max_columns) {
+  if (!ctx) return ERR_INVALID;
+  ctx->c.hash_quad_max = max_columns;
   return OK;
 }
 

@@ -214,11 +214,171 @@ __global__ void hash_column_list_kernel(const Fr* __restrict__ cols, size_t rows
   dst[1] = make_uint4(h[4], h[5], h[6], h[7]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Four lanes per column ("quad" kernel) for FEW columns.
+// BLAKE2s over one column is a sequential chain of R/2 compressions.  With n/G columns per GPU (8 192 at G = 8:
+// 1.7 warps per SM under the thread-per-column kernel) nothing hides that chain, and one warp issuing all eight
+// G functions of a round is held by its own sub-partition's ALU pipe (640 xor/rotate warp instructions at 2 cycles
+// each per compression).  Here lane i of a group of four owns state column i (v[i], v[4+i], v[8+i], v[12+i]): a round
+// is one G on the columns, three shuffles to diagonalise, one G on the diagonals, three shuffles back -- a quarter of
+// the ALU work per warp, spread over four times as many warps and therefore over all four sub-partitions, so the
+// pace is the dependent chain itself (measured, 16 388 rows: 1 580 cycles per compression alone, 1 800 with 8 192
+// columns on the GPU, against 2 270 for the thread-per-column kernel at any column count up to 16 384).  The message block of a column is staged through shared memory (double
+// buffered, one LDG.128 per lane per block, issued one block ahead; each lane then reads the four words its two G's
+// need per round at per-lane addresses kept in registers).  The shuffles and the per-lane LDS share the SM's one
+// LSU/crossbar (about 1.7 cycles per warp instruction), which makes this variant SLOWER than thread-per-column from
+// 16 384 columns on (12.0 against 9.5 ms); hash_columns_range() picks by column count (Ctx::hash_quad_max).
+// ------------------------------------------------------------------------------------------------
+#define LG_B2S_SIGMA                                                                                                 \
+  {                                                                                                                  \
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},     \
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},     \
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},     \
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},     \
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}      \
+  }
+__constant__ uint8_t kB2sSigma[10][16] = LG_B2S_SIGMA;
+__constant__ uint32_t kB2sIV[8] = {0x6A09E667u, 0xBB67AE85u, 0x3C6EF372u, 0xA54FF53Au,
+                                   0x510E527Fu, 0x9B05688Cu, 0x1F83D9ABu, 0x5BE0CD19u};
+
+constexpr int kQuadWarps = 2;          // warps per CTA (1, 2, 4 measured: 7.52, 7.52, 7.69 ms at 8 192 columns)
+constexpr int kQuadColWords = 36;      // shared-memory words per column: 2 buffers x 16 message words + 4 padding
+constexpr int kQuadL2Ahead = 6;
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
+#define B2S_GQ(x, y)               \
+  do {                             \
+    a = a + b + (x);               \
+    d = rotr32(d ^ a, 16);         \
+    c = c + d;                     \
+    b = rotr32(b ^ c, 12);         \
+    a = a + b + (y);               \
+    d = rotr32(d ^ a, 8);          \
+    c = c + d;                     \
+    b = rotr32(b ^ c, 7);          \
+  } while (0)
+
+// One compression of the quad's column.  Lane j keeps b_j for the whole round: the diagonal step of G index i runs
+// in lane j = i + 1 on (a_{j-1}, b_j, c_{j+1}, d_{j+2}), so what travels between the two half rounds is a, c and d --
+// the words a G finishes first -- and the shuffle of the word it finishes last (b, which also opens the next G) is
+// never on the dependent chain.
+// maddr[r][0..3] = shared addresses (buffer 0) of this lane's message words for the column step (x, y) and the
+// diagonal step (x, y) of round r; boff = byte offset of the buffer in use.  (Reading all 16 words with four LDS.128
+// and picking the lane's word with selects was measured too: 8.26 ms against 7.70 ms at 8 192 columns -- the selects
+// land on the ALU pipe.)
+__device__ __forceinline__ void blake2s_compress_quad(uint32_t& h_lo, uint32_t& h_hi, const uint32_t (&maddr)[10][4],
+                                                      uint32_t boff, uint32_t iv_c, uint32_t iv_d, uint32_t t_sel,
+                                                      int i) {
+  uint32_t a = h_lo, b = h_hi, c = iv_c, d = iv_d ^ t_sel;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t x0 = lds_u32(maddr[r][0] + boff), y0 = lds_u32(maddr[r][1] + boff);
+    const uint32_t x1 = lds_u32(maddr[r][2] + boff), y1 = lds_u32(maddr[r][3] + boff);
+    B2S_GQ(x0, y0);
+    a = __shfl_sync(0xffffffffu, a, (i + 3) & 3, 4);
+    d = __shfl_sync(0xffffffffu, d, (i + 2) & 3, 4);
+    c = __shfl_sync(0xffffffffu, c, (i + 1) & 3, 4);
+    B2S_GQ(x1, y1);
+    a = __shfl_sync(0xffffffffu, a, (i + 1) & 3, 4);
+    d = __shfl_sync(0xffffffffu, d, (i + 2) & 3, 4);
+    c = __shfl_sync(0xffffffffu, c, (i + 3) & 3, 4);
+  }
+  h_lo ^= a ^ c;
+  h_hi ^= b ^ d;
+}
+
+template <bool PREFIX>
+__global__ void __launch_bounds__(32 * kQuadWarps) hash_columns_quad_kernel(const Fr* __restrict__ u, size_t rows, int log_k,
+                                                                            int rho, uint8_t* __restrict__ leaves) {
+  __shared__ __align__(16) uint32_t sm[kQuadWarps * 8 * kQuadColWords];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t k = (size_t)1 << log_k, ncols = (size_t)rho * k;
+  const size_t pc0 = ((size_t)blockIdx.x * kQuadWarps + warp) * 8;  // first of this warp's 8 physical columns
+  if (pc0 >= ncols) return;                                           // whole warps only (k is a multiple of 8)
+  const size_t s = pc0 >> log_k, c0 = pc0 & (k - 1);
+  const Fr* base = u + s * rows * k + c0;
+  const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
+  const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
+  const uint32_t sm_warp = (uint32_t)__cvta_generic_to_shared(sm + warp * 8 * kQuadColWords);
+
+  // ---- compute role: lane (q, i) = G index i of column q
+  const int q = lane >> 2, i = lane & 3;
+  const uint32_t sm_col = sm_warp + 4u * kQuadColWords * q;
+  uint32_t maddr[10][4];
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    maddr[r][0] = sm_col + 4u * kB2sSigma[r][2 * i];
+    maddr[r][1] = sm_col + 4u * kB2sSigma[r][2 * i + 1];
+    maddr[r][2] = sm_col + 4u * kB2sSigma[r][8 + 2 * ((i + 3) & 3)];  // lane j runs diagonal G index j - 1
+    maddr[r][3] = sm_col + 4u * kB2sSigma[r][8 + 2 * ((i + 3) & 3) + 1];
+  }
+  const uint32_t iv_c = kB2sIV[i], iv_d = kB2sIV[4 + i];
+  uint32_t h_lo = iv_c ^ (i == 0 ? 0x01010020u : 0u), h_hi = iv_d;
+
+  // ---- load role: lane (lrow, lcol, lhalf) fetches 16 bytes: half `lhalf` of the element of column lcol in row
+  // 2b + lrow -- lanes 0..15 read 256 contiguous bytes of one row, lanes 16..31 of the next
+  const int lrow = lane >> 4, lcol = (lane >> 1) & 7, lhalf = lane & 1;
+  const uint4* src = reinterpret_cast<const uint4*>(base + lcol) + lhalf;  // + row * (2k) uint4
+  const size_t pitch4 = 2 * k;
+  const uint32_t sm_lcol = sm_warp + 4u * kQuadColWords * lcol;
+  // message words this lane supplies: with the 8-byte length prefix a block is [carry(2) | row 2b (8) | row 2b+1 (6)]
+  // and the last two words of row 2b+1 are carried into the next block by the lane that loaded them
+  const bool carrier = PREFIX && lrow == 1 && lhalf == 1;
+  const uint32_t w0 = PREFIX ? (2 + 8 * lrow + 4 * lhalf) : (8 * lrow + 4 * lhalf);
+  const uint32_t st0 = sm_lcol + 4u * w0;                            // first two words of the 16 bytes
+  const uint32_t st1 = carrier ? sm_lcol : st0 + 8u;                 // second two (or the carried pair -> words 0,1)
+  uint32_t cy0 = (uint32_t)rows, cy1 = (uint32_t)((uint64_t)rows >> 32);  // block 0 opens with u64_le(R)
+
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if ((size_t)lrow < rows) v = src[(size_t)lrow * pitch4];
+  for (uint64_t b = 0; b < nblocks; b++) {
+    const uint32_t boff = (uint32_t)(b & 1) * 64u;
+    if (carrier) {
+      sts_v2(st0 + boff, v.x, v.y);
+      sts_v2(st1 + boff, cy0, cy1);
+      cy0 = v.z;
+      cy1 = v.w;
+    } else {
+      sts_v2(st0 + boff, v.x, v.y);
+      sts_v2(st1 + boff, v.z, v.w);
+    }
+    const size_t rn = 2 * (b + 1) + lrow;  // this lane's row of the next block
+    v = make_uint4(0, 0, 0, 0);
+    if (rn < rows) v = src[rn * pitch4];
+    if (rn + 2 * kQuadL2Ahead < rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (rn + 2 * kQuadL2Ahead) * pitch4));
+    __syncwarp();
+    const bool last = (b + 1 == nblocks);
+    const uint64_t t = last ? total : 64 * (b + 1);
+    const uint32_t t_sel = i == 0 ? (uint32_t)t : i == 1 ? (uint32_t)(t >> 32) : (i == 2 && last) ? 0xffffffffu : 0u;
+    blake2s_compress_quad(h_lo, h_hi, maddr, boff, iv_c, iv_d, t_sel, i);
+  }
+  const size_t col = c0 + q;
+  uint32_t* dst = reinterpret_cast<uint32_t*>(leaves + 32 * ((size_t)rho * col + s));  // logical column rho*c + s
+  dst[i] = h_lo;
+  dst[4 + i] = h_hi;
+}
+
 int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u, size_t rows, int log_k, int rho_inv, size_t row0,
                        size_t row_end, uint32_t* state, uint8_t* leaves, bool len_prefix) {
   if (row0 >= row_end || row_end > rows || ((row0 > 0 || row_end < rows) && !state))
     return set_error(ctx, ERR_INVALID, "column hashing tile out of range, or a partial tile without a state buffer");
   const size_t n = (size_t)rho_inv << log_k;
+  if (row0 == 0 && row_end == rows && log_k >= 3 && n <= ctx->hash_quad_max) {
+    const unsigned grid = (unsigned)((n / 8 + kQuadWarps - 1) / kQuadWarps), bs = 32 * kQuadWarps;
+    if (len_prefix) hash_columns_quad_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, leaves);
+    else hash_columns_quad_kernel<false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, leaves);
+    ctx->launches++;
+    LG_CUDA(ctx, cudaGetLastError());
+    return OK;
+  }
   const unsigned bs = 64;
   const unsigned grid = (unsigned)((n + bs - 1) / bs);
   if (len_prefix) hash_columns_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);

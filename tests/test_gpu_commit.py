@@ -184,3 +184,49 @@ def test_tile_wise_hashing_without_length_prefixes(gpu_ctx, prefix):
         cm.free()
     finally:
         gpu_ctx.set_formats(1, 1)
+
+
+@pytest.mark.parametrize("R,k,rho", [(1, 8, 8), (2, 8, 4), (3, 16, 8), (8, 8, 8), (13, 64, 8), (24, 32, 2), (5, 1024, 8)])
+@pytest.mark.parametrize("prefix", [True, False])
+def test_both_column_hash_kernels_match_oracle(gpu_ctx, R, k, rho, prefix):
+    """the thread-per-column kernel and the four-lanes-per-column kernel (few columns: one rank's range on 4-8 GPUs)
+    give the oracle's leaves for odd and even row counts, with and without the length prefix."""
+    rnd = random.Random(R * 7919 + k + rho)
+    msg = rand_matrix(rnd, R, k, (1,) if R > 2 else ())
+    dk, dn = O.Domain(k), O.Domain(rho * k)
+    u = [dn.fft(dk.ifft(r)) for r in msg]
+    fmt = O.Formats(col_len_prefix=prefix, leaf_len_prefix=True)
+    leaves = [O.column_hash([u[i][j] for i in range(R)], O.FR, fmt) for j in range(rho * k)]
+    flat = fr_to_limbs([x for row in msg for x in row])
+    gpu_ctx.set_formats(prefix, True)
+    try:
+        cm = gpu_ctx.encode(flat, R, k, rho)
+        for quad_max in (0, 1 << 30):
+            gpu_ctx.set_hash_quad_max(quad_max)
+            cm.hash()
+            got = cm.read_leaves()
+            assert [bytes(x) for x in got] == leaves, f"quad_max={quad_max}"
+        cm.free()
+    finally:
+        gpu_ctx.set_formats(True, True)
+        gpu_ctx.set_hash_quad_max(8192)
+
+
+def test_column_hash_kernels_agree_on_a_tall_matrix(gpu_ctx):
+    """4 101 rows x 8 192 columns (the per-rank column range of the 2^20-gate matrix on 2 GPUs): same root either way,
+    and the root of the C oracle."""
+    from oracle import cref
+    R, k, rho = 4101, 1024, 8
+    a = np.random.default_rng(5).integers(0, 2 ** 62, size=(R * k, 4), dtype=np.uint64)
+    a[:, 3] &= (1 << 60) - 1
+    ref = cref.commit(a, R, k, rho)
+    cm = gpu_ctx.encode(a, R, k, rho)
+    try:
+        roots = []
+        for quad_max in (0, 1 << 30):
+            gpu_ctx.set_hash_quad_max(quad_max)
+            roots.append(cm.hash())
+        assert roots[0] == roots[1] == ref["root"]
+    finally:
+        gpu_ctx.set_hash_quad_max(8192)
+        cm.free()
