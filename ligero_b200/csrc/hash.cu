@@ -34,16 +34,16 @@ __device__ __forceinline__ uint32_t rotr32(uint32_t x, int n) { return __funnels
 __device__ uint32_t g_b2s_one = 1;
 #define add_fma(a, b) ((a) * b2s_one + (b))
 
-#define B2S_G(a, b, c, d, x, y)        \
-  do {                                 \
-    a = add_fma(add_fma(a, b), (x));   \
-    d = rotr32(d ^ a, 16);             \
-    c = add_fma(c, d);                 \
-    b = rotr32(b ^ c, 12);             \
-    a = add_fma(add_fma(a, b), (y));   \
-    d = rotr32(d ^ a, 8);              \
-    c = add_fma(c, d);                 \
-    b = rotr32(b ^ c, 7);              \
+#define B2S_G(a, b, c, d, x, y)                                \
+  do {                                                         \
+    a = FMA ? add_fma(add_fma(a, b), (x)) : a + b + (x);       \
+    d = rotr32(d ^ a, 16);                                     \
+    c = FMA ? add_fma(c, d) : c + d;                           \
+    b = rotr32(b ^ c, 12);                                     \
+    a = FMA ? add_fma(add_fma(a, b), (y)) : a + b + (y);       \
+    d = rotr32(d ^ a, 8);                                      \
+    c = FMA ? add_fma(c, d) : c + d;                           \
+    b = rotr32(b ^ c, 7);                                      \
   } while (0)
 
 #define B2S_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
@@ -58,6 +58,9 @@ __device__ uint32_t g_b2s_one = 1;
     B2S_G(v3, v4, v9, v14, m[s14], m[s15]);                                              \
   } while (0)
 
+// FMA: additions as multiply-adds on the FMA pipe (enough warps to fill the ALU pipe); otherwise plain additions
+// (three-input IADD3: fewer instructions and a shorter dependent chain, for the few-warps regime)
+template <bool FMA>
 __device__ __forceinline__ void blake2s_compress(uint32_t (&h)[8], const uint32_t (&m)[16], uint64_t t, bool last,
                                                  const uint32_t b2s_one) {
   uint32_t v0 = h[0], v1 = h[1], v2 = h[2], v3 = h[3], v4 = h[4], v5 = h[5], v6 = h[6], v7 = h[7];
@@ -94,7 +97,7 @@ __device__ __forceinline__ void blake2s_init(uint32_t (&h)[8]) {
 // are still arriving over NVLink).  Rows at or beyond `row_lim` are not read.
 constexpr int kHashL2Ahead = 6;  // blocks (pairs of rows) prefetched into L2 ahead of the register prefetch
 
-template <bool PREFIX, bool MONT>
+template <bool PREFIX, bool MONT, bool FMA = true>
 __device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride, size_t rows, size_t row_lim, uint64_t b0,
                                                    uint64_t b1, bool have_pend, uint32_t (&h)[8], uint32_t& c0,
                                                    uint32_t& c1, Fr& pend) {
@@ -136,7 +139,7 @@ __device__ __forceinline__ void hash_column_blocks(const Fr* col, size_t stride,
     }
     const bool last = (b + 1 == nblocks);
     const uint64_t t = last ? total : 64 * (b + 1);
-    blake2s_compress(h, m, t, last, b2s_one);
+    blake2s_compress<FMA>(h, m, t, last, b2s_one);
   }
   pend = n0;  // row 2*b1 if the tile ends on it (odd row_lim), else unused
 }
@@ -154,7 +157,7 @@ __device__ __forceinline__ void hash_one_column(const Fr* col, size_t stride, si
 // rows [row0, row_end) of every column.  `state` carries (h[8], c0, c1, pend[8]) per physical column between
 // tiles, word-major so a warp's accesses coalesce; the tile that ends at `rows` writes the leaves.
 constexpr int kHashStateWords = 18;
-template <bool PREFIX>
+template <bool PREFIX, bool FMA>
 __global__ void __launch_bounds__(64) hash_columns_kernel(const Fr* __restrict__ u, size_t rows, int log_k, int rho,
                                                           size_t row0, size_t row_end, uint32_t* __restrict__ state,
                                                           uint8_t* __restrict__ leaves) {
@@ -184,7 +187,7 @@ __global__ void __launch_bounds__(64) hash_columns_kernel(const Fr* __restrict__
   const size_t lim = row_end < rows ? row_end : rows;
   const uint64_t b0 = row0 / 2, b1 = last ? nblocks : row_end / 2;
   // every plane of a committed matrix holds plain integers (Matrix): no conversion here
-  hash_column_blocks<PREFIX, false>(u + s * rows * k + c, k, rows, lim, b0, b1, have_pend, h, c0, c1, pend);
+  hash_column_blocks<PREFIX, false, FMA>(u + s * rows * k + c, k, rows, lim, b0, b1, have_pend, h, c0, c1, pend);
   if (!last) {
 #pragma unroll
     for (int i = 0; i < 8; i++) state[(size_t)i * ncols + pc] = h[i];
@@ -381,8 +384,14 @@ int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u, size_t rows, int 
   }
   const unsigned bs = 64;
   const unsigned grid = (unsigned)((n + bs - 1) / bs);
-  if (len_prefix) hash_columns_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
-  else hash_columns_kernel<false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+  // at most one warp per SM sub-partition: the warp is bound by its own dependent chain and instruction count, so
+  // plain additions win (8.16 against 9.52 ms at 16 384 columns x 16 388 rows); with more warps the ALU pipe is the
+  // bound and the additions belong on the FMA pipe (26.5 against 30.0 ms at 65 536 columns)
+  const bool fma = n > (size_t)128 * ctx->sm_count;
+  if (len_prefix && fma) hash_columns_kernel<true, true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+  else if (len_prefix) hash_columns_kernel<true, false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+  else if (fma) hash_columns_kernel<false, true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+  else hash_columns_kernel<false, false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;

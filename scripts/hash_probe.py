@@ -9,7 +9,7 @@ from ligero_b200.backend import check
 ctx = Context(0)
 st = torch.cuda.ExternalStream(ctx.stream)
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 16388
-for k in (256, 512, 1024, 2048):
+for k in (1024, 2048, 4096, 8192):
     # the hash only reads U: any bytes will do (plane layout, rho_inv = 8)
     u = torch.randint(0, 2 ** 62, (8 * R * k, 4), dtype=torch.int64, device="cuda")
     cm = ctx.wrap(u, R, k, 8)
