@@ -237,6 +237,12 @@ int lg_sponge_absorb_bytes(lg_sponge* s, const uint8_t* data, size_t len); /* ab
 int lg_sponge_absorb_fr(lg_sponge* s, const uint64_t* elems, size_t count); /* absorb(&Vec<F>) */
 int lg_sponge_squeeze_bytes(lg_sponge* s, uint8_t* out, size_t len);
 
+/* Seeded random Add/Mul circuit of exactly `gates` (>= 4) gates for the synthetic benchmark configurations (SURVEY 8d:
+ * two variables, fair-coin gate types, depth O(log gates), every node feeds the single Add output of value 1, no gate
+ * with two constant operands; sol_len = gates + 4).  Not part of the reference, whose tests build circuits by hand.
+ * output: the output node; var_idx[2] / var_vals[8]: the satisfying assignment (Montgomery limbs). */
+int lg_circuit_synthetic(size_t gates, uint64_t seed, lg_circuit** out, size_t* output, size_t var_idx[2], uint64_t var_vals[8]);
+
 /* ---- LigeroCircuit: src/ligero/mod.rs ---------------------------------------------------------------- */
 typedef struct lg_ligero lg_ligero;
 typedef struct lg_proof lg_proof;
@@ -248,6 +254,17 @@ int lg_ligero_params(const lg_ligero* l, size_t* m, size_t* k, size_t* n, size_t
 /* witness layout of prove_inner, 476-516: out = Fr[4*m*k] (host) = [X;Y;Z;W].  bump != 0: indices refer to
  * the caller's circuit (as in `prove`), 0: to the formatted circuit (as in `prove_inner`). */
 int lg_ligero_witness_matrix(lg_ligero* l, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, uint64_t* out);
+/* The same matrix produced in HBM: evaluation_trace_multioutput (src/arithmetic_circuit/mod.rs:325-358)
+ * as a level-by-level device evaluation that writes every value straight into its slot of [X;Y;Z;W];
+ * out_dev = Fr[4*m*k] on the device.  Only the variable assignment crosses PCIe.  Same failure behaviour as above. */
+int lg_ligero_witness_matrix_dev(lg_ligero* l, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump,
+                                 uint64_t* out_dev);
+/* Where lg_prove runs the trace: -1 (default) = on the device when the circuit is wide (>= 2^16 gates and >= 256 gates
+ * per level on average; a level costs a launch or a CTA barrier, so deep thin circuits are evaluated by the host loop),
+ * 0 = host evaluator + upload, 1 = device.  The resulting matrix is the same either way. */
+int lg_ligero_set_trace_mode(lg_ligero* l, int mode);
+/* gates, levels, kernel launches of one device trace, and whether lg_prove currently uses it */
+int lg_ligero_trace_info(const lg_ligero* l, size_t* gates, size_t* levels, size_t* launches, int* on_device);
 /* prove, 435-455 (bump != 0) / prove_inner, 457-578 (bump == 0); the sponge is advanced in place */
 int lg_prove(lg_ligero* l, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out);
 /* prove_with_labels, 580-611 */

@@ -33,6 +33,10 @@ SIGNATURES = {
     "lg_ctx_set_timing": (c_int, [c_void_p, c_int]),
     "lg_ctx_set_overlap": (c_int, [c_void_p, c_int]),
     "lg_ctx_set_hash_quad_max": (c_int, [c_void_p, c_size_t]),
+    "lg_circuit_synthetic": (c_int, [c_size_t, c_uint64, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_size_t), c_void_p]),
+    "lg_ligero_witness_matrix_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "lg_ligero_set_trace_mode": (c_int, [c_void_p, c_int]),
+    "lg_ligero_trace_info": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int)]),
     "lg_ctx_phase_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_uint64), c_int]),
     "lg_commit": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, c_void_p, POINTER(c_void_p)]),
     "lg_recommit": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -111,6 +111,20 @@ class ArithmeticCircuit:
     def scalar_product(self, left: Sequence[int], right: Sequence[int]) -> int:
         return self.add_nodes([self.mul(l, r) for l, r in zip(left, right)])
 
+    @classmethod
+    def synthetic(cls, gates: int, seed: int = 1):
+        """lg_circuit_synthetic: seeded random Add/Mul circuit of exactly `gates` gates (SURVEY 8d rules).
+        Returns (circuit, output node, [(variable index, value)])."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        h, out = c_void_p(), c_size_t()
+        vidx = (c_size_t * 2)()
+        vals = np.zeros((2, 4), dtype=np.uint64)
+        check(self.lib.lg_circuit_synthetic(gates, seed, byref(h), byref(out), vidx, _ptr(vals)), None, "lg_circuit_synthetic")
+        self.handle = h
+        v = limbs_to_fr(vals)
+        return self, out.value, [(int(vidx[0]), v[0]), (int(vidx[1]), v[1])]
+
     def _counts(self):
         a, b, c, d = c_size_t(), c_size_t(), c_size_t(), c_size_t()
         self.lib.lg_circuit_counts(self.handle, byref(a), byref(b), byref(c), byref(d))
@@ -290,6 +304,26 @@ class LigeroCircuit:
         check(self.lib.lg_ligero_witness_matrix(self.handle, _ptr(idx), _ptr(vals), len(idx), int(bump), _ptr(out)),
               self.ctx.handle, "witness layout")
         return out
+
+    def witness_matrix_device(self, var_assignment: Sequence[Tuple[int, int]], bump: bool = True):
+        """lg_ligero_witness_matrix_dev: evaluation trace + [X;Y;Z;W] layout on the GPU; returns a torch int64 tensor
+        (4*m*k, 4) resident in HBM (Montgomery limbs), usable as the input of Context.commit / prove_matrix."""
+        import torch
+        idx = np.array([i for i, _ in var_assignment], dtype=np.uint64)
+        vals = fr_to_limbs([v for _, v in var_assignment])
+        out = torch.empty((4 * self.m * self.k, 4), dtype=torch.int64, device=f"cuda:{self.ctx.device}")
+        check(self.lib.lg_ligero_witness_matrix_dev(self.handle, _ptr(idx), _ptr(vals), len(idx), int(bump), _ptr(out)),
+              self.ctx.handle, "device witness layout")
+        return out
+
+    def set_trace_mode(self, mode: int):
+        """-1: device trace for wide circuits (default), 0: host evaluator, 1: device."""
+        check(self.lib.lg_ligero_set_trace_mode(self.handle, mode), self.ctx.handle, "set_trace_mode")
+
+    def trace_info(self) -> Dict[str, int]:
+        g, lv, la, dev = c_size_t(), c_size_t(), c_size_t(), c_int()
+        check(self.lib.lg_ligero_trace_info(self.handle, byref(g), byref(lv), byref(la), byref(dev)), self.ctx.handle)
+        return {"gates": g.value, "levels": lv.value, "launches": la.value, "on_device": bool(dev.value)}
 
     def prove(self, var_assignment: Sequence[Tuple[int, int]], sponge: PoseidonSponge) -> LigeroProof:
         idx = np.array([i for i, _ in var_assignment], dtype=np.uint64)

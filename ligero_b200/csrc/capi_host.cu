@@ -67,6 +67,12 @@ struct lg_ligero {
   bool one_found = false;
   size_t m = 0, k = 0, n = 0, t = 0, sol_len = 0;
   lg_constraints* a = nullptr;
+  // evaluation trace on the device (trace.cu): level schedule, reachability from the outputs, witness slots
+  lg::TraceSchedule trace;
+  std::vector<uint32_t> index_map;  // node -> slot in the X/Y/Z/W blocks (0xffffffff for dropped constants)
+  std::vector<uint8_t> reach;       // node feeds an output
+  bool all_gates_reach = true;
+  int trace_mode = -1;              // -1: by circuit shape, 0: host evaluator, 1: device
 };
 
 struct lg_proof {
@@ -306,6 +312,127 @@ int build_constraints(lg_ligero* L, std::string& err) {
   }
   return lg_constraints_create(L->ctx, mk, col_ptr.data(), row_idx.data(), val_id.data(), trip.size(),
                                table.empty() ? nullptr : (const uint64_t*)table.data(), table.size(), &L->a);
+}
+
+// ---- level schedule of the circuit for the device evaluator (trace.cu) ----------------------------------
+constexpr size_t kNarrowLevel = 2048;  // levels of at most this many gates are walked by a single CTA
+
+template <class T>
+int upload(lg_ctx* ctx, const std::vector<T>& v, T** out) {
+  *out = nullptr;
+  if (v.empty()) return OK;
+  if (cudaMalloc((void**)out, v.size() * sizeof(T)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, ERR_NOMEM, "out of device memory for the circuit schedule");
+  }
+  if (cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail(ctx, ERR_CUDA, "schedule upload failed");
+  return OK;
+}
+
+int build_trace(lg_ligero* L) {
+  const lg_circuit& c = L->circuit;
+  const auto& nodes = c.nodes;
+  const size_t N = nodes.size();
+  if (N >= 0x7fffffffu) return fail(L->ctx, ERR_UNSUPPORTED, "circuits of 2^31 nodes or more are not supported");
+  cudaSetDevice(L->ctx->c.device);
+  // node -> witness slot (mod.rs:483-504: constants other than node 0 own no slot)
+  L->index_map.assign(N, 0xffffffffu);
+  L->index_map[0] = 0;
+  size_t seen = 0;
+  for (size_t i = 1; i < N; i++) {
+    if (nodes[i].type == N_CONST) seen++;
+    else L->index_map[i] = (uint32_t)(i - seen);
+  }
+  // which nodes feed an output (the reference panics at prove time on any that does not, mod.rs:476-478)
+  L->reach.assign(N, 0);
+  for (size_t o : L->outputs) L->reach[o] = 1;
+  L->all_gates_reach = true;
+  for (size_t i = N; i-- > 0;) {
+    const Node& nd = nodes[i];
+    if (nd.type != N_ADD && nd.type != N_MUL) continue;
+    if (L->reach[i]) L->reach[nd.l] = L->reach[nd.r] = 1;
+    else L->all_gates_reach = false;
+  }
+  // levels: operands always precede a gate (ArithmeticCircuit only appends), so one forward sweep
+  std::vector<uint32_t> level(N, 0);
+  uint32_t depth = 0;
+  size_t n_gates = 0;
+  for (size_t i = 0; i < N; i++) {
+    const Node& nd = nodes[i];
+    if (nd.type != N_ADD && nd.type != N_MUL) continue;
+    level[i] = 1 + std::max(level[nd.l], level[nd.r]);
+    depth = std::max(depth, level[i]);
+    n_gates++;
+  }
+  lg::TraceSchedule& t = L->trace;
+  t.n_nodes = N;
+  t.n_gates = n_gates;
+  t.n_levels = depth;
+  t.mk = L->m * L->k;
+  // counting sort by (level, Add before Mul)
+  std::vector<uint32_t> start(2 * (size_t)depth + 1, 0);
+  for (size_t i = 0; i < N; i++)
+    if (nodes[i].type == N_ADD || nodes[i].type == N_MUL) start[2 * (level[i] - 1) + (nodes[i].type == N_MUL) + 1]++;
+  for (size_t b = 0; b < 2 * (size_t)depth; b++) start[b + 1] += start[b];
+  std::vector<uint32_t> level_start(depth + 1);
+  for (size_t l = 0; l <= depth; l++) level_start[l] = start[2 * l];
+  std::vector<uint32_t> gnode(n_gates), gl(n_gates), gr(n_gates), gpos(n_gates);
+  {
+    std::vector<uint32_t> cursor(start.begin(), start.end() - 1);
+    for (size_t i = 0; i < N; i++) {
+      const Node& nd = nodes[i];
+      if (nd.type != N_ADD && nd.type != N_MUL) continue;
+      const uint32_t g = cursor[2 * (level[i] - 1) + (nd.type == N_MUL)]++;
+      gnode[g] = (uint32_t)i | (nd.type == N_MUL ? 0x80000000u : 0u);
+      gl[g] = (uint32_t)nd.l;
+      gr[g] = (uint32_t)nd.r;
+      gpos[g] = L->index_map[i];
+    }
+  }
+  std::vector<uint32_t> cnode, cpos;
+  std::vector<Fq> cval;
+  for (size_t i = 0; i < N; i++)
+    if (nodes[i].type == N_CONST) {
+      cnode.push_back((uint32_t)i);
+      cpos.push_back(L->index_map[i]);
+      cval.push_back(c.const_values[nodes[i].l]);
+    }
+  t.n_consts = cnode.size();
+  // segments: wide levels get a launch each, runs of narrow levels share a single-CTA launch
+  t.segments.clear();
+  for (size_t l = 0; l < depth;) {
+    const size_t width = level_start[l + 1] - level_start[l];
+    if (width > kNarrowLevel) {
+      t.segments.push_back({false, l, l + 1, level_start[l], level_start[l + 1]});
+      l++;
+    } else {
+      size_t e = l;
+      while (e < depth && (size_t)(level_start[e + 1] - level_start[e]) <= kNarrowLevel) e++;
+      t.segments.push_back({true, l, e, level_start[l], level_start[e]});
+      l = e;
+    }
+  }
+  LG_TRY(upload(L->ctx, gnode, &t.gate_node));
+  LG_TRY(upload(L->ctx, gl, &t.gate_l));
+  LG_TRY(upload(L->ctx, gr, &t.gate_r));
+  LG_TRY(upload(L->ctx, gpos, &t.gate_pos));
+  LG_TRY(upload(L->ctx, level_start, &t.level_start));
+  LG_TRY(upload(L->ctx, cnode, &t.const_node));
+  LG_TRY(upload(L->ctx, cpos, &t.const_pos));
+  LG_TRY(upload(L->ctx, cval, (Fq**)&t.const_val));
+  if (cudaMalloc((void**)&t.vals, N * sizeof(Fq)) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(L->ctx, ERR_NOMEM, "out of device memory for the value table");
+  }
+  return OK;
+}
+
+// by default the trace runs on the device when the circuit is wide enough for it: a level costs a launch (or a
+// CTA-wide barrier), so deep and thin circuits (R1CS-compiled ones) are evaluated faster by the host loop
+bool trace_on_device(const lg_ligero* L) {
+  if (L->trace_mode >= 0) return L->trace_mode != 0;
+  return L->trace.n_gates >= ((size_t)1 << 16) && L->trace.n_levels * 256 <= L->trace.n_gates;
 }
 
 // ---- openings -----------------------------------------------------------------------------------------
@@ -681,6 +808,88 @@ int lg_circuit_from_r1cs(size_t n_constraints, size_t n_cols, const uint64_t* co
   return OK;
 }
 
+// Seeded random Add/Mul circuit of exactly `gates` gates for the synthetic configurations: two input
+// variables, gate type by a fair coin, operands drawn uniformly from all earlier non-constant nodes (depth O(log gates)
+// with overwhelming probability), every node feeds the single output, the output is an Add gate of value 1
+// (Add(sum, constant 1 - sum)), no gate has two constant operands.  sol_len of the LigeroCircuit is gates + 4.
+// Generator: splitmix64(seed); not part of the reference (its tests build circuits by hand).
+int lg_circuit_synthetic(size_t gates, uint64_t seed, lg_circuit** out, size_t* output, size_t var_idx[2], uint64_t var_vals[8]) {
+  if (!out || !output || !var_idx || !var_vals || gates < 4) return ERR_INVALID;
+  lg_circuit* c = new (std::nothrow) lg_circuit();
+  if (!c) return ERR_NOMEM;
+  uint64_t st = seed;
+  auto next = [&]() {
+    uint64_t z = (st += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+  };
+  auto below = [&](uint64_t n) { return (uint64_t)(((unsigned __int128)next() * n) >> 64); };
+  size_t one;
+  lg_circuit_constant(c, lgh::kOne.l, &one);
+  std::vector<Fq> vals;      // value of every node
+  std::vector<uint8_t> used;  // node is an operand of a later gate
+  vals.reserve(gates + 8);
+  used.reserve(gates + 8);
+  vals.push_back(lgh::kOne);
+  used.push_back(1);
+  for (int v = 0; v < 2; v++) {
+    Fq x;
+    for (int j = 0; j < 4; j++) x.l[j] = next();
+    x.l[3] &= (1ULL << 60) - 1;  // < 2^252 < r: a valid Montgomery residue
+    lg_circuit_new_variable(c, nullptr, &var_idx[v]);
+    memcpy(var_vals + 4 * v, x.l, 32);
+    vals.push_back(x);
+    used.push_back(0);
+  }
+  size_t n_gates = 0, unused = 2;
+  auto gate = [&](bool mul, size_t l, size_t r) {
+    size_t idx;
+    push_gate(c, mul ? N_MUL : N_ADD, l, r, &idx);
+    vals.push_back(mul ? lgh::mul(vals[l], vals[r]) : lgh::add(vals[l], vals[r]));
+    used.push_back(0);
+    for (size_t o : {l, r})
+      if (!used[o]) {
+        used[o] = 1;
+        unused--;
+      }
+    unused++;
+    n_gates++;
+    return idx;
+  };
+  // random part: afterwards a balanced sum over the `unused` nodes takes unused - 1 Add gates, then one closing Add
+  while (n_gates + unused < gates) {
+    const size_t hi = vals.size();
+    size_t l = 1 + below(hi - 1), r = 1 + below(hi - 1);
+    if (n_gates + unused + 1 == gates) {
+      // exactly one more is wanted: a gate that consumes exactly one unused node (total grows by 1, not by 2)
+      size_t u = hi - 1;  // the newest node is always unused
+      size_t v = 1;
+      while (v < hi && (!used[v] || v == u)) v++;
+      l = u;
+      r = v;
+    }
+    gate((next() & 1) != 0, l, r);
+  }
+  std::vector<size_t> level;
+  for (size_t i = 1; i < vals.size(); i++)
+    if (!used[i]) level.push_back(i);
+  while (level.size() > 1) {
+    std::vector<size_t> nxt;
+    for (size_t i = 0; i + 1 < level.size(); i += 2) nxt.push_back(gate(false, level[i], level[i + 1]));
+    if (level.size() & 1) nxt.push_back(level.back());
+    level.swap(nxt);
+  }
+  const Fq k = lgh::sub(lgh::kOne, vals[level[0]]);
+  size_t kc;
+  lg_circuit_constant(c, k.l, &kc);
+  size_t o;
+  push_gate(c, N_ADD, level[0], kc, &o);
+  *output = o;
+  *out = c;
+  return OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // sponge
 // ---------------------------------------------------------------------------------------------------
@@ -823,6 +1032,11 @@ int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs,
     lg_ligero_free(L);
     return s;
   }
+  s = build_trace(L);
+  if (s != OK) {
+    lg_ligero_free(L);
+    return s;
+  }
   *out = L;
   return OK;
 }
@@ -830,8 +1044,77 @@ int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs,
 int lg_ligero_free(lg_ligero* L) {
   if (!L) return OK;
   if (L->a) lg_constraints_free(L->a);
+  cudaSetDevice(L->ctx->c.device);
+  lg::trace_free(L->trace);
   delete L;
   return OK;
+}
+
+int lg_ligero_set_trace_mode(lg_ligero* L, int mode) {
+  if (!L || mode < -1 || mode > 1) return ERR_INVALID;
+  L->trace_mode = mode;
+  return OK;
+}
+
+int lg_ligero_trace_info(const lg_ligero* L, size_t* gates, size_t* levels, size_t* launches, int* on_device) {
+  if (!L) return ERR_INVALID;
+  if (gates) *gates = L->trace.n_gates;
+  if (levels) *levels = L->trace.n_levels;
+  if (launches) *launches = L->trace.segments.size();
+  if (on_device) *on_device = trace_on_device(L) ? 1 : 0;
+  return OK;
+}
+
+// a1 on the device: evaluation trace by levels + scatter into [X;Y;Z;W], all in HBM (out_dev: Fr[4*m*k], device)
+int lg_ligero_witness_matrix_dev(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump,
+                                 uint64_t* out_dev) {
+  if (!L || !out_dev || (n_vars && (!var_idx || !var_vals))) return ERR_INVALID;
+  if (!lg::is_device_ptr(out_dev)) return fail(L->ctx, ERR_INVALID, "lg_ligero_witness_matrix_dev needs a device buffer");
+  const lg_circuit& c = L->circuit;
+  const size_t N = c.nodes.size();
+  std::map<uint32_t, Fq> given;  // a repeated index keeps its last value, as the host evaluator does
+  for (size_t i = 0; i < n_vars; i++) {
+    const size_t idx = bump ? bump_index(L->one_index, L->one_found, var_idx[i]) : var_idx[i];
+    if (idx >= N || c.nodes[idx].type != N_VAR) return fail(L->ctx, ERR_INVALID, "Value supplied for non-variable node");
+    Fq v;
+    memcpy(v.l, var_vals + 4 * i, 32);
+    given[(uint32_t)idx] = v;
+  }
+  bool missing_unreached = false;
+  for (size_t i = 0; i < N; i++)
+    if (c.nodes[i].type == N_VAR) {
+      if (!given.count((uint32_t)i)) {
+        if (L->reach[i]) return fail(L->ctx, ERR_INVALID, "Uninitialised variable");
+        missing_unreached = true;
+      }
+    }
+  if (missing_unreached || !L->all_gates_reach)
+    return fail(L->ctx, ERR_INVALID,
+                "Uninitialised variable. Make sure the circuit only contains nodes upon which the final output truly depends");
+  lg::Ctx* cx = &L->ctx->c;
+  cudaSetDevice(cx->device);
+  std::vector<uint32_t> vnode, vpos;
+  std::vector<Fq> vval;
+  for (const auto& kv : given) {
+    vnode.push_back(kv.first);
+    vpos.push_back(L->index_map[kv.first]);
+    vval.push_back(kv.second);
+  }
+  const size_t nv = vnode.size();
+  uint8_t* buf = nullptr;
+  if (nv) {
+    LG_CUDA(cx, cudaMalloc((void**)&buf, nv * (8 + sizeof(Fq))));
+    LG_CUDA(cx, cudaMemcpyAsync(buf, vval.data(), nv * sizeof(Fq), cudaMemcpyHostToDevice, cx->stream));
+    LG_CUDA(cx, cudaMemcpyAsync(buf + nv * sizeof(Fq), vnode.data(), nv * 4, cudaMemcpyHostToDevice, cx->stream));
+    LG_CUDA(cx, cudaMemcpyAsync(buf + nv * (sizeof(Fq) + 4), vpos.data(), nv * 4, cudaMemcpyHostToDevice, cx->stream));
+  }
+  int s = lg::trace_run(cx, L->trace, (const uint32_t*)(buf + nv * sizeof(Fq)), (const uint32_t*)(buf + nv * (sizeof(Fq) + 4)),
+                        (const lg::Fr*)buf, nv, (lg::Fr*)out_dev);
+  if (buf) {
+    cudaStreamSynchronize(cx->stream);  // the staging vectors above go out of scope
+    cudaFree(buf);
+  }
+  return s;
 }
 
 int lg_ligero_params(const lg_ligero* L, size_t* m, size_t* k, size_t* n, size_t* t, size_t* sol_len) {
@@ -933,6 +1216,16 @@ int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, l
 // LigeroCircuit::prove (bump = 1: indices refer to the caller's circuit) / prove_inner (bump = 0)
 int lg_prove(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out) {
   if (!L || !sponge || !out) return ERR_INVALID;
+  if (trace_on_device(L)) {  // wide circuit: trace + layout in HBM, nothing but the variables crosses PCIe
+    lg::Ctx* cx = &L->ctx->c;
+    cudaSetDevice(cx->device);
+    uint64_t* pre_dev = nullptr;
+    LG_CUDA(cx, cudaMalloc((void**)&pre_dev, 4 * L->m * L->k * sizeof(Fq)));
+    int s = lg_ligero_witness_matrix_dev(L, var_idx, var_vals, n_vars, bump, pre_dev);
+    if (s == OK) s = lg_prove_matrix(L, pre_dev, sponge, out);
+    cudaFree(pre_dev);
+    return s;
+  }
   std::vector<Fq> pre(4 * L->m * L->k);
   LG_TRY(lg_ligero_witness_matrix(L, var_idx, var_vals, n_vars, bump, (uint64_t*)pre.data()));
   return lg_prove_matrix(L, (const uint64_t*)pre.data(), sponge, out);

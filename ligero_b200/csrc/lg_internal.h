@@ -170,4 +170,26 @@ int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u_planes, size_t row
 // BLAKE2s of `count` explicit columns (each `rows` contiguous Montgomery elements)
 int hash_column_list(Ctx* ctx, const Fr* cols, size_t rows, size_t count, uint8_t* digests, bool len_prefix);
 
+// ---- evaluation trace + witness layout on the device (trace.cu; a1 of SURVEY 8a) --------------------------
+// Built once per circuit by lg_ligero_new.  Gates are sorted by level (Add before Mul inside a level); the high bit
+// of gate_node marks a Mul.  `pos` = the node's slot in each of the X/Y/Z/W blocks (its index once the constants
+// other than node 0 are dropped, src/ligero/mod.rs:483-504).
+struct TraceSegment {
+  bool narrow;      // true: levels [lv0, lv1) walked by one CTA; false: one level = gates [g0, g1), thread per gate
+  size_t lv0, lv1, g0, g1;
+};
+struct TraceSchedule {
+  size_t n_nodes = 0, n_gates = 0, n_consts = 0, n_levels = 0, mk = 0;
+  uint32_t *gate_node = nullptr, *gate_l = nullptr, *gate_r = nullptr, *gate_pos = nullptr;  // n_gates each
+  uint32_t* level_start = nullptr;                                                           // n_levels + 1
+  uint32_t *const_node = nullptr, *const_pos = nullptr;                                      // n_consts
+  Fr* const_val = nullptr;
+  Fr* vals = nullptr;                                                                        // n_nodes (value table)
+  std::vector<TraceSegment> segments;
+};
+// out = [X;Y;Z;W] (4*mk elements, device); the variables come as device arrays (node, slot, value)
+int trace_run(Ctx* ctx, const TraceSchedule& t, const uint32_t* var_node, const uint32_t* var_pos, const Fr* var_val,
+              size_t n_vars, Fr* out);
+void trace_free(TraceSchedule& t);
+
 }  // namespace lg
