@@ -250,6 +250,9 @@ typedef struct lg_proof lg_proof;
  * built and uploaded once).  LG_ERR_UNSUPPORTED for gates with two constant operands (the reference panics). */
 int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_ligero** out);
 int lg_ligero_free(lg_ligero* l);
+/* A LigeroCircuit keeps the device buffers of its last proof (codeword matrix, leaves, tree, [X;Y;Z;W]) so that the next
+ * proof of the same circuit re-encodes into them; this returns them to the driver (lg_ligero_free does so too). */
+int lg_ligero_release_buffers(lg_ligero* l);
 int lg_ligero_params(const lg_ligero* l, size_t* m, size_t* k, size_t* n, size_t* t, size_t* sol_len);
 /* witness layout of prove_inner, 476-516: out = Fr[4*m*k] (host) = [X;Y;Z;W].  bump != 0: indices refer to
  * the caller's circuit (as in `prove`), 0: to the formatted circuit (as in `prove_inner`). */
@@ -265,6 +268,9 @@ int lg_ligero_witness_matrix_dev(lg_ligero* l, const size_t* var_idx, const uint
 int lg_ligero_set_trace_mode(lg_ligero* l, int mode);
 /* gates, levels, kernel launches of one device trace, and whether lg_prove currently uses it */
 int lg_ligero_trace_info(const lg_ligero* l, size_t* gates, size_t* levels, size_t* launches, int* on_device);
+/* host wall clock of the last successful lg_prove / lg_prove_matrix on this circuit, ms: [0] trace + layout (lg_prove
+ * only), [1] commit, [2] interleaved test, [3] linear test, [4] quadratic test, [5] the three openings, [6] whole call */
+int lg_ligero_prove_ms(const lg_ligero* l, double ms_out[7]);
 /* prove, 435-455 (bump != 0) / prove_inner, 457-578 (bump == 0); the sponge is advanced in place */
 int lg_prove(lg_ligero* l, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out);
 /* prove_with_labels, 580-611 */

@@ -35,6 +35,8 @@ SIGNATURES = {
     "lg_ctx_set_hash_quad_max": (c_int, [c_void_p, c_size_t]),
     "lg_circuit_synthetic": (c_int, [c_size_t, c_uint64, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_size_t), c_void_p]),
     "lg_ligero_witness_matrix_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "lg_ligero_prove_ms": (c_int, [c_void_p, POINTER(c_double)]),
+    "lg_ligero_release_buffers": (c_int, [c_void_p]),
     "lg_ligero_set_trace_mode": (c_int, [c_void_p, c_int]),
     "lg_ligero_trace_info": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_int)]),
     "lg_ctx_phase_ms": (c_int, [c_void_p, POINTER(c_double), POINTER(c_uint64), c_int]),

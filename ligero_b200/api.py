@@ -320,6 +320,18 @@ class LigeroCircuit:
         """-1: device trace for wide circuits (default), 0: host evaluator, 1: device."""
         check(self.lib.lg_ligero_set_trace_mode(self.handle, mode), self.ctx.handle, "set_trace_mode")
 
+    def release_buffers(self):
+        """return the device buffers kept between proofs of this circuit (lg_ligero_release_buffers)"""
+        check(self.lib.lg_ligero_release_buffers(self.handle), self.ctx.handle)
+
+    PROVE_PHASES = ("trace", "commit", "interleaved", "linear", "quadratic", "openings", "total")
+
+    def prove_ms(self) -> Dict[str, float]:
+        """host wall clock (ms) of the phases of the last prove on this circuit"""
+        ms = (ctypes.c_double * 7)()
+        check(self.lib.lg_ligero_prove_ms(self.handle, ms), self.ctx.handle)
+        return {p: ms[i] for i, p in enumerate(self.PROVE_PHASES)}
+
     def trace_info(self) -> Dict[str, int]:
         g, lv, la, dev = c_size_t(), c_size_t(), c_size_t(), c_int()
         check(self.lib.lg_ligero_trace_info(self.handle, byref(g), byref(lv), byref(la), byref(dev)), self.ctx.handle)

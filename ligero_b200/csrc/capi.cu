@@ -46,6 +46,22 @@ int ctx_scratch(Ctx* ctx, size_t bytes, void** out) {
   return OK;
 }
 
+int ctx_host_stage(Ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->host_stage_bytes) {
+    if (ctx->host_stage) {
+      LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      LG_CUDA(ctx, cudaFreeHost(ctx->host_stage));
+      ctx->host_stage = nullptr;
+      ctx->host_stage_bytes = 0;
+    }
+    cudaError_t e = cudaHostAlloc(&ctx->host_stage, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return set_error(ctx, ERR_NOMEM, std::string("pinned staging cudaHostAlloc: ") + cudaGetErrorString(e));
+    ctx->host_stage_bytes = bytes;
+  }
+  *out = ctx->host_stage;
+  return OK;
+}
+
 // true if p is device (or managed) memory
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes at;
@@ -386,6 +402,16 @@ int lg_ctx_create(int device, lg_ctx** out) {
     return ERR_CUDA;
   }
   cudaDeviceGetAttribute(&ctx->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  {
+    // the tests allocate their temporaries (up to two 4mk-element vectors) stream-ordered; keep freed blocks in the
+    // pool instead of returning them to the driver at every synchronisation, or each proof pays the allocation again
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   if (const char* e = getenv("LG_OVERLAP")) ctx->c.overlap = atoi(e) != 0;  // tuning hook; see lg_ctx_set_overlap
   if (const char* e = getenv("LG_HASH_QUAD_MAX")) ctx->c.hash_quad_max = (size_t)strtoull(e, nullptr, 10);
   *out = ctx;
@@ -417,6 +443,7 @@ int lg_ctx_destroy(lg_ctx* ctx) {
     if (ctx->c.hash_state) cudaFree(ctx->c.hash_state);
   }
   if (ctx->c.tile_cosets) cudaFree(ctx->c.tile_cosets);
+  if (ctx->c.host_stage) cudaFreeHost(ctx->c.host_stage);
   for (auto& m : ctx->c.marks) cudaEventDestroy(m.second);
   for (auto& e : ctx->c.event_pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->c.stream);

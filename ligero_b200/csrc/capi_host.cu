@@ -9,6 +9,7 @@
 // points of capi.cu / capi_protocol.cu on the GPU; this file only sequences the Fiat-Shamir transcript.
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -71,8 +72,17 @@ struct lg_ligero {
   lg::TraceSchedule trace;
   std::vector<uint32_t> index_map;  // node -> slot in the X/Y/Z/W blocks (0xffffffff for dropped constants)
   std::vector<uint8_t> reach;       // node feeds an output
+  std::vector<uint32_t> var_nodes;  // every Variable node
   bool all_gates_reach = true;
   int trace_mode = -1;              // -1: by circuit shape, 0: host evaluator, 1: device
+  // host wall clock of the last prove, ms: trace+layout, commit, interleaved test, linear test, quadratic test,
+  // the three openings together, whole call (every phase ends on a device-to-host copy, so these are synchronised)
+  double prove_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+  // device buffers kept between proofs of this circuit (allocating and freeing 36 GiB per proof at 2^24 gates costs
+  // more than the three tests together): the codeword matrix with its leaves and tree, and the [X;Y;Z;W] matrix of
+  // the device trace.  lg_ligero_release_buffers / lg_ligero_free return them.
+  lg_matrix* u_cache = nullptr;
+  uint64_t* pre_cache = nullptr;
 };
 
 struct lg_proof {
@@ -392,6 +402,9 @@ int build_trace(lg_ligero* L) {
   }
   std::vector<uint32_t> cnode, cpos;
   std::vector<Fq> cval;
+  L->var_nodes.clear();
+  for (size_t i = 0; i < N; i++)
+    if (nodes[i].type == N_VAR) L->var_nodes.push_back((uint32_t)i);
   for (size_t i = 0; i < N; i++)
     if (nodes[i].type == N_CONST) {
       cnode.push_back((uint32_t)i);
@@ -444,15 +457,18 @@ int open_columns(lg_ligero* L, lg_matrix* U, lgh::PoseidonSponge& sponge, Opened
   int log_n = 0;
   while (((size_t)1 << log_n) < L->n) log_n++;
   const size_t depth = (size_t)(log_n - 1);
-  std::vector<Fq> cols(L->t * rows);
+  // t x R elements (82 MB at 2^24 gates): device -> pinned staging at full PCIe rate, then one pass into the proof
+  void* stage = nullptr;
+  LG_TRY(lg::ctx_host_stage(&L->ctx->c, L->t * rows * sizeof(Fq), &stage));
+  const Fq* cols = (const Fq*)stage;
   std::vector<uint8_t> sib(L->t * 32), auth(L->t * depth * 32 + 1);
-  LG_TRY(lg_open(U, idx.data(), L->t, (uint64_t*)cols.data(), sib.data(), auth.data()));
+  LG_TRY(lg_open(U, idx.data(), L->t, (uint64_t*)stage, sib.data(), auth.data()));
   out.columns.resize(L->t);
   out.leaf_index = idx;
   out.sibling.resize(L->t);
   out.auth.assign(L->t, std::vector<Digest>(depth));
   for (size_t q = 0; q < L->t; q++) {
-    out.columns[q].assign(cols.begin() + q * rows, cols.begin() + (q + 1) * rows);
+    out.columns[q].assign(cols + q * rows, cols + (q + 1) * rows);
     memcpy(out.sibling[q].data(), sib.data() + 32 * q, 32);
     for (size_t d = 0; d < depth; d++) memcpy(out.auth[q][d].data(), auth.data() + 32 * (q * depth + d), 32);
   }
@@ -1041,8 +1057,22 @@ int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs,
   return OK;
 }
 
+int lg_ligero_release_buffers(lg_ligero* L) {
+  if (!L) return ERR_INVALID;
+  cudaSetDevice(L->ctx->c.device);
+  if (L->u_cache) lg_matrix_free(L->u_cache);
+  L->u_cache = nullptr;
+  if (L->pre_cache) {
+    cudaStreamSynchronize(L->ctx->c.stream);
+    cudaFree(L->pre_cache);
+  }
+  L->pre_cache = nullptr;
+  return OK;
+}
+
 int lg_ligero_free(lg_ligero* L) {
   if (!L) return OK;
+  lg_ligero_release_buffers(L);
   if (L->a) lg_constraints_free(L->a);
   cudaSetDevice(L->ctx->c.device);
   lg::trace_free(L->trace);
@@ -1053,6 +1083,12 @@ int lg_ligero_free(lg_ligero* L) {
 int lg_ligero_set_trace_mode(lg_ligero* L, int mode) {
   if (!L || mode < -1 || mode > 1) return ERR_INVALID;
   L->trace_mode = mode;
+  return OK;
+}
+
+int lg_ligero_prove_ms(const lg_ligero* L, double ms_out[7]) {
+  if (!L || !ms_out) return ERR_INVALID;
+  for (int i = 0; i < 7; i++) ms_out[i] = L->prove_ms[i];
   return OK;
 }
 
@@ -1081,12 +1117,10 @@ int lg_ligero_witness_matrix_dev(lg_ligero* L, const size_t* var_idx, const uint
     given[(uint32_t)idx] = v;
   }
   bool missing_unreached = false;
-  for (size_t i = 0; i < N; i++)
-    if (c.nodes[i].type == N_VAR) {
-      if (!given.count((uint32_t)i)) {
-        if (L->reach[i]) return fail(L->ctx, ERR_INVALID, "Uninitialised variable");
-        missing_unreached = true;
-      }
+  for (const uint32_t i : L->var_nodes)
+    if (!given.count(i)) {
+      if (L->reach[i]) return fail(L->ctx, ERR_INVALID, "Uninitialised variable");
+      missing_unreached = true;
     }
   if (missing_unreached || !L->all_gates_reach)
     return fail(L->ctx, ERR_INVALID,
@@ -1173,19 +1207,37 @@ int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, l
   const size_t rows = 4 * L->m, k = L->k;
   lg_proof* P = new (std::nothrow) lg_proof();
   if (!P) return ERR_NOMEM;
-  lg_matrix* U = nullptr;
-  int s = lg_commit(ctx, preenc_u, rows, k, 8, P->root.data(), &U);  // mod.rs:521-551
+  typedef std::chrono::steady_clock Clock;
+  const Clock::time_point t_begin = Clock::now();
+  Clock::time_point t_last = t_begin;
+  double open_ms = 0;
+  auto lap = [&]() {
+    const Clock::time_point now = Clock::now();
+    const double ms = std::chrono::duration<double, std::milli>(now - t_last).count();
+    t_last = now;
+    return ms;
+  };
+  lg_matrix* U = L->u_cache;
+  int s;
+  if (U) {
+    s = lg_recommit(U, preenc_u, P->root.data());  // mod.rs:521-551 into the resident buffers
+  } else {
+    s = lg_commit(ctx, preenc_u, rows, k, 8, P->root.data(), &U);
+    if (s == OK) L->u_cache = U;
+  }
   auto done = [&](int code) {
-    if (U) lg_matrix_free(U);
     if (code != OK) {
       delete P;
     } else {
+      L->prove_ms[5] = open_ms;
+      L->prove_ms[6] = std::chrono::duration<double, std::milli>(Clock::now() - t_begin).count();
       *out = P;
     }
     return code;
   };
   if (s != OK) return done(s);
   sp.absorb_bytes(P->root.data(), 32);  // 560
+  L->prove_ms[1] = lap();
   // Test-Interleaved (646-669)
   std::vector<uint8_t> seed = sp.squeeze_bytes(32);
   std::vector<Fq> r(rows);
@@ -1193,7 +1245,9 @@ int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, l
   P->preenc_u_lc.resize(k);
   if ((s = lg_row_combine(U, (const uint64_t*)r.data(), (uint64_t*)P->preenc_u_lc.data())) != OK) return done(s);
   sp.absorb_field(P->preenc_u_lc);
+  L->prove_ms[2] = lap();
   if ((s = open_columns(L, U, sp, P->interleaved)) != OK) return done(s);
+  open_ms += lap();
   // Test-Linear-Constraints (712-747)
   seed = sp.squeeze_bytes(32);
   std::vector<Fq> poly(2 * k);
@@ -1201,7 +1255,9 @@ int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, l
   if ((s = lg_linear_test_seeded(U, L->a, seed.data(), (uint64_t*)poly.data(), &len)) != OK) return done(s);
   P->linear_poly.assign(poly.begin(), poly.begin() + len);
   sp.absorb_field(P->linear_poly);
+  L->prove_ms[3] = lap();
   if ((s = open_columns(L, U, sp, P->linear)) != OK) return done(s);
+  open_ms += lap();
   // Test-Quadratic-Constraints (832-859)
   seed = sp.squeeze_bytes(32);
   std::vector<Fq> rq(L->m);
@@ -1209,26 +1265,45 @@ int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, l
   if ((s = lg_quadratic_test(U, (const uint64_t*)rq.data(), (uint64_t*)poly.data(), &len)) != OK) return done(s);
   P->quadratic_poly.assign(poly.begin(), poly.begin() + len);
   sp.absorb_field(P->quadratic_poly);
+  L->prove_ms[4] = lap();
   if ((s = open_columns(L, U, sp, P->quadratic)) != OK) return done(s);
+  open_ms += lap();
   return done(OK);
 }
 
 // LigeroCircuit::prove (bump = 1: indices refer to the caller's circuit) / prove_inner (bump = 0)
 int lg_prove(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out) {
   if (!L || !sponge || !out) return ERR_INVALID;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto trace_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+  int s;
   if (trace_on_device(L)) {  // wide circuit: trace + layout in HBM, nothing but the variables crosses PCIe
     lg::Ctx* cx = &L->ctx->c;
     cudaSetDevice(cx->device);
-    uint64_t* pre_dev = nullptr;
-    LG_CUDA(cx, cudaMalloc((void**)&pre_dev, 4 * L->m * L->k * sizeof(Fq)));
-    int s = lg_ligero_witness_matrix_dev(L, var_idx, var_vals, n_vars, bump, pre_dev);
-    if (s == OK) s = lg_prove_matrix(L, pre_dev, sponge, out);
-    cudaFree(pre_dev);
+    if (!L->pre_cache) LG_CUDA(cx, cudaMalloc((void**)&L->pre_cache, 4 * L->m * L->k * sizeof(Fq)));
+    uint64_t* pre_dev = L->pre_cache;
+    s = lg_ligero_witness_matrix_dev(L, var_idx, var_vals, n_vars, bump, pre_dev);
+    double tr = 0;
+    if (s == OK) {
+      cudaStreamSynchronize(cx->stream);
+      tr = trace_ms();
+      s = lg_prove_matrix(L, pre_dev, sponge, out);
+    }
+    if (s == OK) {
+      L->prove_ms[0] = tr;
+      L->prove_ms[6] += tr;
+    }
     return s;
   }
   std::vector<Fq> pre(4 * L->m * L->k);
   LG_TRY(lg_ligero_witness_matrix(L, var_idx, var_vals, n_vars, bump, (uint64_t*)pre.data()));
-  return lg_prove_matrix(L, (const uint64_t*)pre.data(), sponge, out);
+  const double tr = trace_ms();
+  s = lg_prove_matrix(L, (const uint64_t*)pre.data(), sponge, out);
+  if (s == OK) {
+    L->prove_ms[0] = tr;
+    L->prove_ms[6] += tr;
+  }
+  return s;
 }
 
 int lg_prove_with_labels(lg_ligero* L, const char* const* labels, const uint64_t* var_vals, size_t n_vars, lg_sponge* sponge,

@@ -79,32 +79,30 @@ inline Fq sub(const Fq& a, const Fq& b) {
   return r;
 }
 inline Fq neg(const Fq& a) { return sub(kZero, a); }
+// Montgomery product, "no-carry" CIOS: the modulus' top limb leaves two spare bits, so the running sum fits four limbs
+// and the two carry chains (a*b_i and m*r) advance in one pass.  Host side of Fiat-Shamir only (sponge, verifier).
 inline Fq mul(const Fq& a, const Fq& b) {
-  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
-  for (int i = 0; i < 4; i++) {
-    u128 c = 0;
-    for (int j = 0; j < 4; j++) {
-      c += (u128)a.l[j] * b.l[i] + t[j];
-      t[j] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[4] = (uint64_t)c;
-    t[5] = (uint64_t)(c >> 64);
-    const uint64_t m = t[0] * kPInv;
-    c = (u128)m * kP[0] + t[0];
-    c >>= 64;
-    for (int j = 1; j < 4; j++) {
-      c += (u128)m * kP[j] + t[j];
-      t[j - 1] = (uint64_t)c;
-      c >>= 64;
-    }
-    c += t[4];
-    t[3] = (uint64_t)c;
-    t[4] = t[5] + (uint64_t)(c >> 64);
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+#define LGH_MUL_ROUND(bi)                                                \
+  {                                                                      \
+    u128 A = (u128)a.l[0] * (bi) + t0;                                   \
+    const uint64_t m = (uint64_t)A * kPInv;                              \
+    u128 C = (u128)m * kP[0] + (uint64_t)A;                              \
+    A = (u128)a.l[1] * (bi) + t1 + (uint64_t)(A >> 64);                  \
+    C = (u128)m * kP[1] + (uint64_t)A + (uint64_t)(C >> 64);             \
+    t0 = (uint64_t)C;                                                    \
+    A = (u128)a.l[2] * (bi) + t2 + (uint64_t)(A >> 64);                  \
+    C = (u128)m * kP[2] + (uint64_t)A + (uint64_t)(C >> 64);             \
+    t1 = (uint64_t)C;                                                    \
+    A = (u128)a.l[3] * (bi) + t3 + (uint64_t)(A >> 64);                  \
+    C = (u128)m * kP[3] + (uint64_t)A + (uint64_t)(C >> 64);             \
+    t2 = (uint64_t)C;                                                    \
+    t3 = (uint64_t)(C >> 64) + (uint64_t)(A >> 64);                      \
   }
-  Fq r = {{t[0], t[1], t[2], t[3]}};
-  if (t[4] || geq_p(r.l)) sub_p(r.l);
+  LGH_MUL_ROUND(b.l[0]) LGH_MUL_ROUND(b.l[1]) LGH_MUL_ROUND(b.l[2]) LGH_MUL_ROUND(b.l[3])
+#undef LGH_MUL_ROUND
+  Fq r = {{t0, t1, t2, t3}};
+  if (geq_p(r.l)) sub_p(r.l);
   return r;
 }
 inline Fq from_mont(const Fq& a) {
@@ -117,11 +115,23 @@ inline Fq from_u64(uint64_t x) {
   return to_mont(c);
 }
 inline Fq pow_u64(Fq b, uint64_t e) {
+  if (e == 17) {  // the test sponge's S-box: 4 squarings + 1 product
+    const Fq b2 = mul(b, b), b4 = mul(b2, b2), b8 = mul(b4, b4);
+    return mul(mul(b8, b8), b);
+  }
+  if (e == 5) {
+    const Fq b2 = mul(b, b);
+    return mul(mul(b2, b2), b);
+  }
   Fq acc = kOne;
+  bool first = true;
   while (e) {
-    if (e & 1) acc = mul(acc, b);
-    b = mul(b, b);
+    if (e & 1) {
+      acc = first ? b : mul(acc, b);
+      first = false;
+    }
     e >>= 1;
+    if (e) b = mul(b, b);
   }
   return acc;
 }
@@ -207,7 +217,11 @@ struct PoseidonConfig {
 
 class PoseidonSponge {
  public:
-  explicit PoseidonSponge(const PoseidonConfig& cfg) : cfg_(cfg), state_(cfg.rate + cfg.capacity, kZero) {}
+  explicit PoseidonSponge(const PoseidonConfig& cfg) : cfg_(cfg), state_(cfg.rate + cfg.capacity, kZero) {
+    // the permutation runs once per `rate` absorbed elements on the host (Fiat-Shamir is sequential): entries 0 and 1
+    // of the MDS matrix (the test sponge's is all 0/1) cost nothing or one addition instead of a product
+    for (const Fq& e : cfg_.mds) mds_kind_.push_back(e.is_zero() ? 0 : (e == kOne ? 1 : 2));
+  }
   void absorb_field(const std::vector<Fq>& elems) {
     if (elems.empty()) return;
     if (absorbing_) {
@@ -292,24 +306,36 @@ class PoseidonSponge {
   void permute() {
     const int t = cfg_.rate + cfg_.capacity;
     const int half = cfg_.full_rounds / 2;
-    std::vector<Fq> nxt(t);
-    for (int rnd = 0; rnd < cfg_.full_rounds + cfg_.partial_rounds; rnd++) {
-      for (int i = 0; i < t; i++) state_[i] = add(state_[i], cfg_.ark[(size_t)rnd * t + i]);
+    Fq* st = state_.data();
+    nxt_.resize(t);
+    Fq* nxt = nxt_.data();
+    const Fq* ark = cfg_.ark.data();
+    for (int rnd = 0; rnd < cfg_.full_rounds + cfg_.partial_rounds; rnd++, ark += t) {
+      for (int i = 0; i < t; i++) st[i] = add(st[i], ark[i]);
       if (rnd < half || rnd >= half + cfg_.partial_rounds) {
-        for (int i = 0; i < t; i++) state_[i] = pow_u64(state_[i], cfg_.alpha);
+        for (int i = 0; i < t; i++) st[i] = pow_u64(st[i], cfg_.alpha);
       } else {
-        state_[0] = pow_u64(state_[0], cfg_.alpha);
+        st[0] = pow_u64(st[0], cfg_.alpha);
       }
       for (int i = 0; i < t; i++) {
         Fq acc = kZero;
-        for (int j = 0; j < t; j++) acc = add(acc, mul(state_[j], cfg_.mds[(size_t)i * t + j]));
+        bool first = true;
+        const Fq* row = cfg_.mds.data() + (size_t)i * t;
+        const uint8_t* kind = mds_kind_.data() + (size_t)i * t;
+        for (int j = 0; j < t; j++) {
+          if (kind[j] == 0) continue;
+          const Fq term = kind[j] == 1 ? st[j] : mul(st[j], row[j]);
+          acc = first ? term : add(acc, term);
+          first = false;
+        }
         nxt[i] = acc;
       }
-      state_ = nxt;
+      for (int i = 0; i < t; i++) st[i] = nxt[i];
     }
   }
   PoseidonConfig cfg_;
-  std::vector<Fq> state_;
+  std::vector<uint8_t> mds_kind_;  // per MDS entry: 0 = zero, 1 = one, 2 = general
+  std::vector<Fq> state_, nxt_;
   bool absorbing_ = true;
   int index_ = 0;
 };

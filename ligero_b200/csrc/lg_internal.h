@@ -77,6 +77,9 @@ struct Ctx {
   // whole-matrix column hashes of at most this many columns use the four-lanes-per-column kernel (hash.cu);
   // lg_ctx_set_hash_quad_max / LG_HASH_QUAD_MAX override, 0 disables
   size_t hash_quad_max = 8192;
+  // pinned host staging for large device-to-host results (opened columns), grown on demand
+  void* host_stage = nullptr;
+  size_t host_stage_bytes = 0;
   // optional per-phase device timing (CUDA events on `stream`): bench.py's live kernel durations
   bool timing = false;
   std::vector<std::pair<int, cudaEvent_t>> marks;  // (phase that ENDS at this event, event)
@@ -89,6 +92,7 @@ enum Phase : int { PH_BEGIN = -1, PH_NTT_STRIDED_INV = 0, PH_NTT_LOCAL = 1, PH_N
 void phase_mark(Ctx* ctx, int phase_ended);
 
 int ctx_scratch(Ctx* ctx, size_t bytes, void** out);
+int ctx_host_stage(Ctx* ctx, size_t bytes, void** out);  // pinned, reused across calls (one host thread per context)
 // plain: the coset scale factors carry an extra R^-1, so the coset planes come out as plain integers
 int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool plain = false);
 

@@ -24,17 +24,15 @@ for lg in [int(a) for a in sys.argv[1:]] or [16, 20]:
             proof = lc.prove(assign, lb.PoseidonSponge.test_sponge())
             best = min(best, time.perf_counter() - t)
         blobs[name] = proof.to_bytes()
-        # the trace alone
-        ctx.sync()
-        t = time.perf_counter()
-        if mode == 1:
-            w = lc.witness_matrix_device(assign)
-            ctx.sync()
-        else:
-            w = lc.witness_matrix(assign)
-        tw = time.perf_counter() - t
-        del w
-        print(f"  prove ({name}): {best * 1e3:.1f} ms, of which trace + layout {tw * 1e3:.1f} ms; proof {len(blobs[name])} bytes", flush=True)
+        host_phases = lc.prove_ms()
+        ctx.set_timing(True)
+        ctx.phase_ms()
+        lc.prove(assign, lb.PoseidonSponge.test_sponge())
+        dev = ctx.phase_ms()
+        ctx.set_timing(False)
+        print("  device phases (ms): " + ", ".join(f"{k} {v[0]:.2f}" for k, v in dev.items() if v[1]), flush=True)
+        print(f"  prove ({name}): {best * 1e3:.1f} ms; phases of the last one: "
+              + ", ".join(f"{k} {v:.1f}" for k, v in host_phases.items()) + f"; proof {len(blobs[name])} bytes", flush=True)
     t = time.perf_counter()
     ok = lc.verify(proof, lb.PoseidonSponge.test_sponge())
     print(f"  verify: {ok} in {(time.perf_counter() - t) * 1e3:.1f} ms; proofs equal: {blobs['device trace'] == blobs['host trace']}", flush=True)
