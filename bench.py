@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--log-gates", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--prove-log-gates", type=int, nargs="*", default=[20],
+                    help="informational whole-prove legs (LigeroCircuit::prove/verify on seeded synthetic circuits); "
+                         "24 adds ~15 s of host-side circuit set-up")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -361,13 +364,44 @@ def main():
         cpu_baseline = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
                         "sample": f"{rows_s} of {R} rows x k={k} (n={n}), reference schedule, {secs:.1f} s"}
 
+    # ---------------- informational: whole proofs on synthetic circuits (BASELINE configs 3 / 4) ----------------
+    # trace + layout on the device, commit, the three tests, 3 x 156 opened columns, host Fiat-Shamir sponge; wall clock
+    prove_info = {}
+    try:
+        cm.free()
+        del msg
+        torch.cuda.empty_cache()
+        import ligero_b200 as lb
+        for lg in args.prove_log_gates:
+            circ, out, assign = lb.ArithmeticCircuit.synthetic(1 << lg, 2024)
+            lc = lb.LigeroCircuit(ctx, circ, [out])
+            lc.prove(assign, lb.PoseidonSponge.test_sponge())          # allocates the resident buffers
+            best, proof = None, None
+            for _ in range(3):
+                ctx.sync()
+                t0 = time.perf_counter()
+                proof = lc.prove(assign, lb.PoseidonSponge.test_sponge())
+                dt = (time.perf_counter() - t0) * 1e3
+                best = dt if best is None else min(best, dt)
+            phases = lc.prove_ms()
+            t0 = time.perf_counter()
+            ok = lc.verify(proof, lb.PoseidonSponge.test_sponge())
+            vms = (time.perf_counter() - t0) * 1e3
+            prove_info[f"2^{lg}_gates"] = {"prove_ms": best, "verify_ms": vms, "accepted": bool(ok), "m": lc.m, "k": lc.k,
+                                           "n": lc.n, "t": lc.t, "proof_bytes": len(proof.to_bytes()),
+                                           "phase_ms_last": phases, "trace": lc.trace_info()}
+            del proof, lc, circ
+    except Exception as exc:  # informational only
+        prove_info["error"] = str(exc)
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32x8 Montgomery (BN254 Fr)", "data": "synthetic",
         "config": {"workload": workload_name(args.log_gates, R, k, n), "rows": R, "k": k, "n": n, "rho_inv": RHO_INV,
                    "l2_policy": "inputs larger than L2 (4 GiB matrix, 32 GiB codeword matrix per step)",
-                   "codeword_elems_per_s": value * RHO_INV, "witness_shaped": witness_shaped},
+                   "codeword_elems_per_s": value * RHO_INV, "witness_shaped": witness_shaped,
+                   "whole_prove": prove_info},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
