@@ -384,9 +384,12 @@ def main():
                 dt = (time.perf_counter() - t0) * 1e3
                 best = dt if best is None else min(best, dt)
             phases = lc.prove_ms()
-            t0 = time.perf_counter()
-            ok = lc.verify(proof, lb.PoseidonSponge.test_sponge())
-            vms = (time.perf_counter() - t0) * 1e3
+            vms, ok = None, True
+            for _ in range(2):                                         # the first call allocates the verifier's buffers
+                t0 = time.perf_counter()
+                ok = lc.verify(proof, lb.PoseidonSponge.test_sponge()) and ok
+                dt = (time.perf_counter() - t0) * 1e3
+                vms = dt if vms is None else min(vms, dt)
             prove_info[f"2^{lg}_gates"] = {"prove_ms": best, "verify_ms": vms, "accepted": bool(ok), "m": lc.m, "k": lc.k,
                                            "n": lc.n, "t": lc.t, "proof_bytes": len(proof.to_bytes()),
                                            "phase_ms_last": phases, "trace": lc.trace_info()}
