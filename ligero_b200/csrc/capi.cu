@@ -317,6 +317,59 @@ static int encode_tiled(lg_matrix* h, const uint64_t* src, bool host, bool hash)
   return OK;
 }
 
+// The same upload/encode overlap for a rank's row shard (multi-GPU): the local matrix arrives from the host in row
+// tiles while the previous tile is encoded and scattered to the column shards through `map` (row_off selects the
+// tile's rows inside the local [X_g; Y_g; Z_g; W_g] order).
+static int encode_sharded_tiled(lg_ctx* ctx, const uint64_t* src, size_t rows, int log_k, int rho_inv, OutMap map, bool plain) {
+  Ctx* c = &ctx->c;
+  const size_t k = (size_t)1 << log_k, row_bytes = k * sizeof(Fr);
+  size_t tile_rows = (((size_t)256 << 20) / row_bytes) & ~(size_t)1;
+  if (tile_rows < 2) tile_rows = 2;
+  if (tile_rows > rows) tile_rows = rows;
+  const size_t tile_bytes = tile_rows * row_bytes;
+  if (!c->copy_stream) {
+    LG_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+      LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming));
+    }
+  }
+  if (c->stage_bytes < tile_bytes) {
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; i++) {
+      if (c->stage[i]) cudaFree(c->stage[i]);
+      c->stage[i] = nullptr;
+      LG_CUDA(c, cudaMalloc(&c->stage[i], tile_bytes));
+    }
+    c->stage_bytes = tile_bytes;
+  }
+  const size_t cos_bytes = log_k > 10 ? (size_t)(rho_inv - 1) * tile_bytes : 0;
+  if (c->tile_cosets_bytes < cos_bytes) {
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->tile_cosets) cudaFree(c->tile_cosets);
+    c->tile_cosets = nullptr;
+    LG_CUDA(c, cudaMalloc(&c->tile_cosets, cos_bytes));
+    c->tile_cosets_bytes = cos_bytes;
+  }
+  LG_CUDA(c, cudaEventRecord(c->ev_consumed[0], c->stream));
+  LG_CUDA(c, cudaEventRecord(c->ev_consumed[1], c->stream));
+  int t = 0;
+  for (size_t row0 = 0; row0 < rows; row0 += tile_rows, t++) {
+    const size_t nr = row0 + tile_rows <= rows ? tile_rows : rows - row0;
+    const int b = t & 1;
+    LG_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
+    LG_CUDA(c, cudaMemcpyAsync(c->stage[b], (const uint8_t*)src + row0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice,
+                               c->copy_stream));
+    LG_CUDA(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    LG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+    map.row_off = (uint32_t)row0;
+    LG_TRY(encode_rows(c, (const Fr*)c->stage[b], nr, log_k, rho_inv, nullptr, (Fr*)c->tile_cosets, &map, plain));
+    LG_CUDA(c, cudaEventRecord(c->ev_consumed[b], c->stream));
+  }
+  return OK;
+}
+
 static bool tiled_shape(const Matrix& m) {
   return m.rows * m.k * sizeof(Fr) >= ((size_t)64 << 20) && m.rows < ((size_t)1 << 31);
 }
@@ -644,6 +697,8 @@ int lg_encode_sharded(lg_ctx* ctx, const uint64_t* msg_local, size_t m_g, size_t
   map.i0 = (uint32_t)i0;
   map.rows_total = 4ull * m;
   const size_t rows = 4 * m_g;
+  if (!is_device_ptr(msg_local) && rows * k * sizeof(Fr) >= ((size_t)64 << 20) && rows < ((size_t)1 << 31))
+    return encode_sharded_tiled(ctx, msg_local, rows, log_k, (int)rho_inv, map, plain != 0);
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(ctx, msg_local, rows * k, &dev, &to_free));
@@ -678,6 +733,8 @@ int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, 
   map.m = map.m_g = (uint32_t)nrows;  // one block of consecutive global rows: grow(i) = row_base + i
   map.i0 = (uint32_t)row_base;
   map.rows_total = rows_total;
+  if (!is_device_ptr(msg_rows) && nrows * k * sizeof(Fr) >= ((size_t)64 << 20) && nrows < ((size_t)1 << 31))
+    return encode_sharded_tiled(ctx, msg_rows, nrows, log_k, (int)rho_inv, map, plain != 0);
   const Fr* dev;
   void* to_free;
   LG_TRY(stage_input(ctx, msg_rows, nrows * k, &dev, &to_free));

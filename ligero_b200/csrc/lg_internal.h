@@ -122,18 +122,21 @@ struct Matrix {
 // straight into the column shard of the rank that owns its message index c (peer memory over NVLink,
 // mapped with CUDA IPC), at its GLOBAL row position -- the all-to-all is fused into the last NTT pass.
 //   element (plane s, local row i, column c)  ->  base[c >> log_kg] + ((s*rows_total + grow(i)) << log_kg) + (c mod kg)
-//   grow(i) = (i / m_g) * m + i0 + i % m_g     (local rows are [X_g; Y_g; Z_g; W_g], m_g rows per block)
+//   grow(i) = (i / m_g) * m + i0 + i % m_g     (local rows are [X_g; Y_g; Z_g; W_g], m_g rows per block;
+//                                              i = kernel row + row_off when a row tile of them is encoded)
 constexpr int kMaxRanks = 8;
 struct OutMap {
   Fr* base[kMaxRanks];
   int log_kg;
   uint32_t m, m_g, i0;
+  uint32_t row_off;  // the kernel's row 0 is local row row_off (a row tile of the local matrix)
   unsigned long long rows_total;
 };
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t outmap_row(const OutMap& o, uint32_t i_local) {
-  const uint32_t b = i_local / o.m_g;
-  return b * o.m + o.i0 + (i_local - b * o.m_g);
+  const uint32_t il = i_local + o.row_off;
+  const uint32_t b = il / o.m_g;
+  return b * o.m + o.i0 + (il - b * o.m_g);
 }
 __device__ __forceinline__ Fr* outmap_ptr(const OutMap& o, uint32_t s, uint32_t grow, uint32_t c) {
   return o.base[c >> o.log_kg] + ((((unsigned long long)s * o.rows_total + grow) << o.log_kg) + (c & ((1u << o.log_kg) - 1u)));

@@ -33,6 +33,27 @@ for (m, k, rho) in [(3, 8, 8), (5, 64, 8), (86, 128, 8), (33, 2048, 8), (9, 8192
         ok &= same
         cm.free()
     dist.barrier()
+# host (pinned) row shards: the upload is tiled and overlapped with the encoding (lg_encode_sharded[_rows] on host memory)
+for (m, k, rho) in [(1025, 2048, 8), (600, 8192, 8)]:
+    rng = np.random.default_rng(99 + m)
+    ids = par.local_row_ids(m, world, rank)
+    local = rng.integers(0, 2 ** 62, size=(len(ids) * k, 4), dtype=np.uint64)
+    local[:, 3] &= (1 << 60) - 1
+    host = torch.from_numpy(local.view(np.int64)).pin_memory()
+    dev = host.cuda()
+    same = True
+    for mode, pipe in (("fused", True), ("fused", False)):
+        sc = par.ShardedCommitter(ctx, m, k, rho, rank, world, mode, pipe)
+        r_dev = sc.commit(dev)
+        r_host = sc.commit(host)
+        r_host2 = sc.commit(host)
+        same &= r_dev == r_host == r_host2
+        sc.close()
+    flag = torch.tensor([1 if same else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"m={m} k={k} world={world}: host-input (tiled upload) roots {'==' if int(flag.item()) else '!='} device-input roots", flush=True)
+        ok &= bool(int(flag.item()))
 if rank == 0:
     print("MGPU_OK" if ok else "MGPU_FAIL", flush=True)
 dist.destroy_process_group()
