@@ -312,13 +312,18 @@ int build_constraints(lg_ligero* L, std::string& err) {
     }
     row++;
   }
-  std::stable_sort(trip.begin(), trip.end(), [](const Triplet& a, const Triplet& b) { return a.col < b.col; });
+  // CSC by a counting sort on the column (stable: entries of a column keep the order in which the rows produced
+  // them, as a stable sort of the triplets would; 151 M entries at 2^24 gates)
   std::vector<uint32_t> col_ptr(mk + 1, 0), row_idx(trip.size()), val_id(trip.size());
   for (const auto& t : trip) col_ptr[t.col + 1]++;
   for (size_t cidx = 0; cidx < mk; cidx++) col_ptr[cidx + 1] += col_ptr[cidx];
-  for (size_t e = 0; e < trip.size(); e++) {
-    row_idx[e] = trip[e].row;
-    val_id[e] = trip[e].vid;
+  {
+    std::vector<uint32_t> cursor(col_ptr.begin(), col_ptr.end() - 1);
+    for (const auto& t : trip) {
+      const uint32_t e = cursor[t.col]++;
+      row_idx[e] = t.row;
+      val_id[e] = t.vid;
+    }
   }
   return lg_constraints_create(L->ctx, mk, col_ptr.data(), row_idx.data(), val_id.data(), trip.size(),
                                table.empty() ? nullptr : (const uint64_t*)table.data(), table.size(), &L->a);
