@@ -237,6 +237,12 @@ int lg_sponge_absorb_bytes(lg_sponge* s, const uint8_t* data, size_t len); /* ab
 int lg_sponge_absorb_fr(lg_sponge* s, const uint64_t* elems, size_t count); /* absorb(&Vec<F>) */
 int lg_sponge_squeeze_bytes(lg_sponge* s, uint8_t* out, size_t len);
 
+/* The R1CS half of read_constraint_system (src/reader.rs:6-19): an iden3 .r1cs v1 file image (BN254 Fr only,
+ * LG_ERR_UNSUPPORTED for another prime) -> from_constraint_system.  outputs: size_t[outputs_cap >= nConstraints]; call
+ * once with outputs = NULL to learn n_constraints / n_wires (returns LG_ERR_INVALID after filling them).  The witness
+ * half of the reference (ark-circom's wasm witness calculator) is out of scope: the assignment is an input. */
+int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out, size_t* outputs, size_t outputs_cap,
+                               size_t* n_constraints_out, size_t* n_wires_out);
 /* Seeded random Add/Mul circuit of exactly `gates` (>= 4) gates for the synthetic benchmark configurations (SURVEY 8d:
  * two variables, fair-coin gate types, depth O(log gates), every node feeds the single Add output of value 1, no gate
  * with two constant operands; sol_len = gates + 4).  Not part of the reference, whose tests build circuits by hand.

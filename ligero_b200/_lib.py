@@ -33,6 +33,8 @@ SIGNATURES = {
     "lg_ctx_set_timing": (c_int, [c_void_p, c_int]),
     "lg_ctx_set_overlap": (c_int, [c_void_p, c_int]),
     "lg_ctx_set_hash_quad_max": (c_int, [c_void_p, c_size_t]),
+    "lg_circuit_from_r1cs_bytes": (c_int, [c_void_p, c_size_t, POINTER(c_void_p), c_void_p, c_size_t, POINTER(c_size_t),
+                                           POINTER(c_size_t)]),
     "lg_circuit_synthetic": (c_int, [c_size_t, c_uint64, POINTER(c_void_p), POINTER(c_size_t), POINTER(c_size_t), c_void_p]),
     "lg_ligero_witness_matrix_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     "lg_ligero_prove_ms": (c_int, [c_void_p, POINTER(c_double)]),

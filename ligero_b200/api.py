@@ -111,6 +111,28 @@ class ArithmeticCircuit:
     def scalar_product(self, left: Sequence[int], right: Sequence[int]) -> int:
         return self.add_nodes([self.mul(l, r) for l, r in zip(left, right)])
 
+    @staticmethod
+    def from_r1cs_bytes(data: bytes):
+        """read_constraint_system's R1CS half (src/reader.rs): iden3 .r1cs v1 image -> (circuit, outputs, n_wires)."""
+        lib = _lib.load()
+        buf = np.frombuffer(data, dtype=np.uint8)
+        nc, nw, h = c_size_t(), c_size_t(), c_void_p()
+        lib.lg_circuit_from_r1cs_bytes(_ptr(buf), len(buf), byref(h), None, 0, byref(nc), byref(nw))   # sizes only
+        if nc.value == 0:
+            raise LigeroB200Error("not an iden3 .r1cs v1 file over BN254 Fr")
+        outputs = np.zeros(nc.value, dtype=np.uint64)
+        st = lib.lg_circuit_from_r1cs_bytes(_ptr(buf), len(buf), byref(h), _ptr(outputs), nc.value, byref(nc), byref(nw))
+        if st != 0:
+            raise LigeroB200Error(f"from_r1cs_bytes failed with status {st} (malformed file, or an empty row of A, B or C)")
+        c = ArithmeticCircuit.__new__(ArithmeticCircuit)
+        c.lib, c.handle = lib, h
+        return c, [int(x) for x in outputs], nw.value
+
+    @staticmethod
+    def from_r1cs_file(path: str):
+        with open(path, "rb") as f:
+            return ArithmeticCircuit.from_r1cs_bytes(f.read())
+
     @classmethod
     def synthetic(cls, gates: int, seed: int = 1):
         """lg_circuit_synthetic: seeded random Add/Mul circuit of exactly `gates` gates (SURVEY 8d rules).

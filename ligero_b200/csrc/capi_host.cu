@@ -829,6 +829,88 @@ int lg_circuit_from_r1cs(size_t n_constraints, size_t n_cols, const uint64_t* co
   return OK;
 }
 
+// read_constraint_system's R1CS half (src/reader.rs:6-19): the iden3 .r1cs v1 container -> the three
+// matrices as ConstraintSystem::to_matrices yields them (terms of a row merged per wire, zero coefficients dropped, wires
+// ascending, as ark-relations' sorted LinearCombination does) -> from_constraint_system.  The witness half of the
+// reference (a wasm witness calculator run by ark-circom) is out of scope: callers pass the assignment.
+int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out, size_t* outputs, size_t outputs_cap,
+                               size_t* n_constraints_out, size_t* n_wires_out) {
+  if (!data || !out) return ERR_INVALID;
+  auto rd32 = [&](size_t off, uint32_t& v) {
+    if (off + 4 > len) return false;
+    memcpy(&v, data + off, 4);
+    return true;
+  };
+  auto rd64 = [&](size_t off, uint64_t& v) {
+    if (off + 8 > len) return false;
+    memcpy(&v, data + off, 8);
+    return true;
+  };
+  uint32_t version = 0, nsec = 0;
+  if (len < 12 || memcmp(data, "r1cs", 4) != 0 || !rd32(4, version) || !rd32(8, nsec) || version != 1) return ERR_INVALID;
+  size_t off = 12, hdr_off = 0, hdr_len = 0, body_off = 0, body_len = 0;
+  for (uint32_t sct = 0; sct < nsec; sct++) {
+    uint32_t typ;
+    uint64_t size;
+    if (!rd32(off, typ) || !rd64(off + 4, size) || size > len - off - 12) return ERR_INVALID;
+    off += 12;
+    if (typ == 1) {
+      hdr_off = off;
+      hdr_len = size;
+    } else if (typ == 2) {
+      body_off = off;
+      body_len = size;
+    }
+    off += size;
+  }
+  if (!hdr_off || !body_off) return ERR_INVALID;
+  uint32_t fs = 0, n_wires = 0, n_constraints = 0;
+  if (hdr_len < 4 || !rd32(hdr_off, fs) || fs != 32 || hdr_len < 4 + 32 + 16 + 8 + 4) return ERR_INVALID;
+  if (memcmp(data + hdr_off + 4, lgh::kP, 32) != 0) return ERR_UNSUPPORTED;  // only BN254 Fr
+  rd32(hdr_off + 4 + 32, n_wires);
+  rd32(hdr_off + 4 + 32 + 16 + 8, n_constraints);
+  if (n_wires == 0 || n_constraints == 0) return ERR_INVALID;
+  std::vector<uint64_t> row_ptr[3], col_idx[3];
+  std::vector<Fq> coeff[3];
+  size_t o = body_off;
+  const size_t end = body_off + body_len;
+  for (int mtx = 0; mtx < 3; mtx++) row_ptr[mtx].push_back(0);
+  std::map<uint32_t, Fq> acc;
+  for (uint32_t r = 0; r < n_constraints; r++)
+    for (int mtx = 0; mtx < 3; mtx++) {
+      uint32_t nt;
+      if (o + 4 > end || !rd32(o, nt)) return ERR_INVALID;
+      o += 4;
+      if ((size_t)nt * 36 > end - o) return ERR_INVALID;
+      acc.clear();
+      for (uint32_t e = 0; e < nt; e++, o += 36) {
+        uint32_t w;
+        rd32(o, w);
+        if (w >= n_wires) return ERR_INVALID;
+        Fq raw;
+        memcpy(raw.l, data + o + 4, 32);
+        while (lgh::geq_p(raw.l)) lgh::sub_p(raw.l);  // coefficients are canonical in practice; reduce anything else
+        const Fq c = lgh::to_mont(raw);
+        auto it = acc.find(w);
+        if (it == acc.end()) acc[w] = c;
+        else it->second = lgh::add(it->second, c);
+      }
+      for (const auto& kv : acc) {
+        if (kv.second.is_zero()) continue;
+        col_idx[mtx].push_back(kv.first);
+        coeff[mtx].push_back(kv.second);
+      }
+      row_ptr[mtx].push_back(col_idx[mtx].size());
+    }
+  if (n_constraints_out) *n_constraints_out = n_constraints;
+  if (n_wires_out) *n_wires_out = n_wires;
+  if (!outputs || outputs_cap < n_constraints) return ERR_INVALID;
+  const uint64_t* rp[3] = {row_ptr[0].data(), row_ptr[1].data(), row_ptr[2].data()};
+  const uint64_t* ci[3] = {col_idx[0].data(), col_idx[1].data(), col_idx[2].data()};
+  const uint64_t* cf[3] = {(const uint64_t*)coeff[0].data(), (const uint64_t*)coeff[1].data(), (const uint64_t*)coeff[2].data()};
+  return lg_circuit_from_r1cs(n_constraints, n_wires, rp, ci, cf, out, outputs);
+}
+
 // Seeded random Add/Mul circuit of exactly `gates` gates for the synthetic configurations: two input
 // variables, gate type by a fair coin, operands drawn uniformly from all earlier non-constant nodes (depth O(log gates)
 // with overwhelming probability), every node feeds the single output, the output is an Add gate of value 1
