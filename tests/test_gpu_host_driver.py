@@ -186,3 +186,24 @@ def test_witness_matrix_matches_oracle(gpu_ctx):
     want = [x for r in olc.witness_matrix(va) for x in r]
     lc = lb.LigeroCircuit(gpu_ctx, mirror_circuit(oc), outs)
     assert limbs_to_fr(lc.witness_matrix(assign)) == want
+
+
+def test_repeated_squaring_10_proof_equals_oracle(gpu_ctx):
+    """BASELINE config 2: circom/repeated_squaring_10 through from_constraint_system on the GPU prover: proof bytes equal
+    the oracle's, both verifiers accept, a wrong output is rejected."""
+    from tests.util import repeated_squaring_r1cs
+    a, b, c, nw, wit = repeated_squaring_r1cs(10, 3)
+    va = list(enumerate(wit))[1:]
+    oc, oouts = O.ArithmeticCircuit.from_constraint_system(a, b, c, nw)
+    olc = O.LigeroCircuit(oc, oouts)
+    want = wire.serialize_proof(olc.prove(va, osponge()))
+    circ, outs = lb.ArithmeticCircuit.from_constraint_system(a, b, c, nw)
+    assert outs == oouts and circ.num_nodes() == oc.num_nodes()
+    lc = lb.LigeroCircuit(gpu_ctx, circ, outs)
+    proof = lc.prove(va, lb.PoseidonSponge.test_sponge())
+    assert proof.to_bytes() == want
+    assert lc.verify(proof, lb.PoseidonSponge.test_sponge())
+    assert olc.verify(wire.deserialize_proof(proof.to_bytes()), osponge())
+    bad = list(va)
+    bad[0] = (1, (wit[1] + 1) % P)
+    assert not lc.verify(lc.prove(bad, lb.PoseidonSponge.test_sponge()), lb.PoseidonSponge.test_sponge())

@@ -151,3 +151,21 @@ def test_poseidon_shapes_and_witness():
     assert all(v == 1 for v in circ.evaluate_multioutput(va, outs))
     lc = O.LigeroCircuit(circ, outs)
     assert (lc.m, lc.k, lc.n, lc.t) == (86, 128, 1024, 156)
+
+
+def test_repeated_squaring_10_via_from_constraint_system():
+    """BASELINE config 2: circom/repeated_squaring_10 (no .r1cs in the reference: R1CS built by hand, tests/util.py)
+    through from_constraint_system -> prove -> verify; y = x^(2^10); a wrong y is rejected."""
+    from tests.util import repeated_squaring_r1cs
+    a, b, c, nw, wit = repeated_squaring_r1cs(10, 3)
+    assert wit[1] == pow(3, 1 << 10, O.P)
+    circ, outs = O.ArithmeticCircuit.from_constraint_system(a, b, c, nw)
+    va = list(enumerate(wit))[1:]
+    assert circ.evaluate_multioutput(va, outs) == [1] * 10
+    lc = O.LigeroCircuit(circ, outs)
+    sp = lambda: O.PoseidonSponge(O.test_sponge_config())
+    proof = lc.prove(va, sp())
+    assert lc.verify(proof, sp())
+    bad = list(va)
+    bad[0] = (1, (wit[1] + 1) % O.P)
+    assert not lc.verify(lc.prove(bad, sp()), sp())

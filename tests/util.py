@@ -87,3 +87,22 @@ def proofs_equal(a: "O.LigeroProof", b: "O.LigeroProof") -> bool:
     return (a.u_root == b.u_root and a.preenc_u_lc == b.preenc_u_lc and oc_eq(a.interleaved, b.interleaved)
             and a.linear_poly == b.linear_poly and oc_eq(a.linear, b.linear)
             and a.quadratic_poly == b.quadratic_poly and oc_eq(a.quadratic, b.quadratic))
+
+
+def repeated_squaring_r1cs(steps: int = 10, x: int = 3):
+    """R1CS of circom/repeated_squaring_10.circom (lines 19-29: tmp0 <== x*x; tmp_i <== tmp_{i-1}^2; y <== tmp9), built by
+    hand because the reference ships no .r1cs for it: wires [1, y, x, tmp0 .. tmp_{steps-2}] as circom orders
+    them with the linear constraint y = tmp_{steps-1} substituted away, and circom's sign convention (-a) * b = -c, as in
+    the reference's multiplication.r1cs / cube.r1cs.  Returns (A, B, C rows as [(coeff, wire)], n_wires, witness)."""
+    n_wires = 3 + steps - 1
+    wire_of = lambda i: 3 + i if i < steps - 1 else 1          # tmp_i (the last one is the output y)
+    a, b, c = [], [], []
+    prev = 2                                                    # x
+    vals = {0: 1, 2: x % P}
+    for i in range(steps):
+        a.append([(P - 1, prev)])
+        b.append([(1, prev)])
+        c.append([(P - 1, wire_of(i))])
+        vals[wire_of(i)] = vals[prev] * vals[prev] % P
+        prev = wire_of(i)
+    return a, b, c, n_wires, [vals[w] for w in range(n_wires)]
