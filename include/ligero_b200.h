@@ -69,7 +69,7 @@ int lg_ctx_set_timing(lg_ctx* ctx, int enabled);
 int lg_ctx_set_overlap(lg_ctx* ctx, int enabled);
 /* Column hashing has two kernels with identical results: one thread per column (enough columns to fill the
  * SMs' ALU pipes) and four lanes per column (few columns, e.g. one rank's column range on 4-8 GPUs, where the
- * sequential BLAKE2s chain of a column sets the pace).  Whole-matrix hashes of at most max_columns columns use the
+ * sequential BLAKE2s chain of a column sets the pace).  Hashes (whole or by row tiles) of at most max_columns columns use the
  * latter; 0 disables it.  Default 8192 (LG_HASH_QUAD_MAX in the environment overrides). */
 int lg_ctx_set_hash_quad_max(lg_ctx* ctx, size_t max_columns);
 int lg_ctx_phase_ms(lg_ctx* ctx, double* ms_out, uint64_t* count_out, int n);

@@ -300,7 +300,9 @@ __device__ __forceinline__ void blake2s_compress_quad(uint32_t& h_lo, uint32_t& 
 
 template <bool PREFIX>
 __global__ void __launch_bounds__(32 * kQuadWarps) hash_columns_quad_kernel(const Fr* __restrict__ u, size_t rows, int log_k,
-                                                                            int rho, uint8_t* __restrict__ leaves) {
+                                                                            int rho, size_t row0, size_t row_end,
+                                                                            uint32_t* __restrict__ state,
+                                                                            uint8_t* __restrict__ leaves) {
   __shared__ __align__(16) uint32_t sm[kQuadWarps * 8 * kQuadColWords];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t k = (size_t)1 << log_k, ncols = (size_t)rho * k;
@@ -324,7 +326,16 @@ __global__ void __launch_bounds__(32 * kQuadWarps) hash_columns_quad_kernel(cons
     maddr[r][3] = sm_col + 4u * kB2sSigma[r][8 + 2 * ((i + 3) & 3) + 1];
   }
   const uint32_t iv_c = kB2sIV[i], iv_d = kB2sIV[4 + i];
+  // row tile [row0, row_end): same carried state as the thread-per-column kernel (h, carry words, pending odd row),
+  // word-major in `state`; the tile that ends at `rows` writes the leaves
+  const bool first = row0 == 0, last_tile = row_end >= rows, have_pend = (row0 & 1) != 0;
+  const size_t row_lim = row_end < rows ? row_end : rows;
+  const uint64_t b0 = row0 / 2, b1 = last_tile ? nblocks : row_end / 2;
   uint32_t h_lo = iv_c ^ (i == 0 ? 0x01010020u : 0u), h_hi = iv_d;
+  if (!first) {
+    h_lo = state[(size_t)i * ncols + pc0 + q];
+    h_hi = state[(size_t)(4 + i) * ncols + pc0 + q];
+  }
 
   // ---- load role: lane (lrow, lcol, lhalf) fetches 16 bytes: half `lhalf` of the element of column lcol in row
   // 2b + lrow -- lanes 0..15 read 256 contiguous bytes of one row, lanes 16..31 of the next
@@ -339,10 +350,19 @@ __global__ void __launch_bounds__(32 * kQuadWarps) hash_columns_quad_kernel(cons
   const uint32_t st0 = sm_lcol + 4u * w0;                            // first two words of the 16 bytes
   const uint32_t st1 = carrier ? sm_lcol : st0 + 8u;                 // second two (or the carried pair -> words 0,1)
   uint32_t cy0 = (uint32_t)rows, cy1 = (uint32_t)((uint64_t)rows >> 32);  // block 0 opens with u64_le(R)
+  if (!first && carrier) {
+    cy0 = state[8 * ncols + pc0 + lcol];
+    cy1 = state[9 * ncols + pc0 + lcol];
+  }
 
   uint4 v = make_uint4(0, 0, 0, 0);
-  if ((size_t)lrow < rows) v = src[(size_t)lrow * pitch4];
-  for (uint64_t b = 0; b < nblocks; b++) {
+  if (have_pend && lrow == 0) {  // the row that opened the previous tile's unfinished block
+    const size_t w = (size_t)(10 + 4 * lhalf) * ncols + pc0 + lcol;
+    v = make_uint4(state[w], state[w + ncols], state[w + 2 * ncols], state[w + 3 * ncols]);
+  } else if (2 * b0 + lrow < row_lim) {
+    v = src[(2 * b0 + lrow) * pitch4];
+  }
+  for (uint64_t b = b0; b < b1; b++) {
     const uint32_t boff = (uint32_t)(b & 1) * 64u;
     if (carrier) {
       sts_v2(st0 + boff, v.x, v.y);
@@ -355,13 +375,29 @@ __global__ void __launch_bounds__(32 * kQuadWarps) hash_columns_quad_kernel(cons
     }
     const size_t rn = 2 * (b + 1) + lrow;  // this lane's row of the next block
     v = make_uint4(0, 0, 0, 0);
-    if (rn < rows) v = src[rn * pitch4];
-    if (rn + 2 * kQuadL2Ahead < rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (rn + 2 * kQuadL2Ahead) * pitch4));
+    if (rn < row_lim) v = src[rn * pitch4];
+    if (rn + 2 * kQuadL2Ahead < row_lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (rn + 2 * kQuadL2Ahead) * pitch4));
     __syncwarp();
     const bool last = (b + 1 == nblocks);
     const uint64_t t = last ? total : 64 * (b + 1);
     const uint32_t t_sel = i == 0 ? (uint32_t)t : i == 1 ? (uint32_t)(t >> 32) : (i == 2 && last) ? 0xffffffffu : 0u;
     blake2s_compress_quad(h_lo, h_hi, maddr, boff, iv_c, iv_d, t_sel, i);
+  }
+  if (!last_tile) {
+    state[(size_t)i * ncols + pc0 + q] = h_lo;
+    state[(size_t)(4 + i) * ncols + pc0 + q] = h_hi;
+    if (carrier) {
+      state[8 * ncols + pc0 + lcol] = cy0;
+      state[9 * ncols + pc0 + lcol] = cy1;
+    }
+    if ((row_end & 1) && lrow == 0) {  // v holds row 2*b1 = row_end - 1, the pending odd row
+      const size_t w = (size_t)(10 + 4 * lhalf) * ncols + pc0 + lcol;
+      state[w] = v.x;
+      state[w + ncols] = v.y;
+      state[w + 2 * ncols] = v.z;
+      state[w + 3 * ncols] = v.w;
+    }
+    return;
   }
   const size_t col = c0 + q;
   uint32_t* dst = reinterpret_cast<uint32_t*>(leaves + 32 * ((size_t)rho * col + s));  // logical column rho*c + s
@@ -374,10 +410,10 @@ int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u, size_t rows, int 
   if (row0 >= row_end || row_end > rows || ((row0 > 0 || row_end < rows) && !state))
     return set_error(ctx, ERR_INVALID, "column hashing tile out of range, or a partial tile without a state buffer");
   const size_t n = (size_t)rho_inv << log_k;
-  if (row0 == 0 && row_end == rows && log_k >= 3 && n <= ctx->hash_quad_max) {
+  if (log_k >= 3 && n <= ctx->hash_quad_max) {
     const unsigned grid = (unsigned)((n / 8 + kQuadWarps - 1) / kQuadWarps), bs = 32 * kQuadWarps;
-    if (len_prefix) hash_columns_quad_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, leaves);
-    else hash_columns_quad_kernel<false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, leaves);
+    if (len_prefix) hash_columns_quad_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+    else hash_columns_quad_kernel<false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
     ctx->launches++;
     LG_CUDA(ctx, cudaGetLastError());
     return OK;

@@ -74,7 +74,7 @@ struct Ctx {
   cudaEvent_t ev_encoded = nullptr, ev_hashed = nullptr;
   uint32_t* hash_state = nullptr;
   size_t hash_state_words = 0;
-  // whole-matrix column hashes of at most this many columns use the four-lanes-per-column kernel (hash.cu);
+  // column hashes (whole or row tiles) of at most this many columns use the four-lanes-per-column kernel (hash.cu);
   // lg_ctx_set_hash_quad_max / LG_HASH_QUAD_MAX override, 0 disables
   size_t hash_quad_max = 8192;
   // pinned host staging for large device-to-host results (opened columns), grown on demand

@@ -156,15 +156,24 @@ def test_tile_wise_column_hashing_matches_oracle(gpu_ctx, R, k, rho, cuts):
     flat = fr_to_limbs([x for row in msg for x in row])
     cm = gpu_ctx.encode(flat, R, k, rho)
     try:
+        for quad_max in (0, 1 << 30):        # thread-per-column tiles, four-lanes-per-column tiles
+            gpu_ctx.set_hash_quad_max(quad_max)
+            bounds = [0] + list(cuts) + [R]
+            for a, b in zip(bounds[:-1], bounds[1:]):
+                cm.hash_rows(a, b)
+            root = cm.hash_finish()
+            assert root == tree.root(), f"quad_max={quad_max}"
+            got_leaves = cm.read_leaves()
+            assert [bytes(x) for x in got_leaves] == leaves, f"quad_max={quad_max}"
+            assert cm.hash() == tree.root()      # the one-shot path on the same matrix
+        # the carried state has one format: tiles may alternate between the two kernels
         bounds = [0] + list(cuts) + [R]
-        for a, b in zip(bounds[:-1], bounds[1:]):
+        for t, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+            gpu_ctx.set_hash_quad_max((1 << 30) if t % 2 == 0 else 0)
             cm.hash_rows(a, b)
-        root = cm.hash_finish()
-        assert root == tree.root()
-        got_leaves = cm.read_leaves()
-        assert [bytes(x) for x in got_leaves] == leaves
-        assert cm.hash() == tree.root()      # the one-shot path on the same matrix
+        assert cm.hash_finish() == tree.root()
     finally:
+        gpu_ctx.set_hash_quad_max(8192)
         cm.free()
 
 
@@ -177,12 +186,17 @@ def test_tile_wise_hashing_without_length_prefixes(gpu_ctx, prefix):
         R, k, rho = 11, 32, 8
         flat = fr_to_limbs([rnd.randrange(P) for _ in range(R * k)])
         cm = gpu_ctx.encode(flat, R, k, rho)
+        gpu_ctx.set_hash_quad_max(0)
         one = cm.hash()
-        for a, b in ((0, 3), (3, 4), (4, 10), (10, 11)):
-            cm.hash_rows(a, b)
-        assert cm.hash_finish() == one
+        for quad_max in (0, 1 << 30):
+            gpu_ctx.set_hash_quad_max(quad_max)
+            for a, b in ((0, 3), (3, 4), (4, 10), (10, 11)):
+                cm.hash_rows(a, b)
+            assert cm.hash_finish() == one
+            assert cm.hash() == one
         cm.free()
     finally:
+        gpu_ctx.set_hash_quad_max(8192)
         gpu_ctx.set_formats(1, 1)
 
 
