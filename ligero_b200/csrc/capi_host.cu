@@ -513,7 +513,21 @@ bool verify_path(const lg_ctx* ctx, const Digest& root, const Digest& leaf, cons
 }
 
 // verify_column_openings (mod.rs:957-996): re-derive the indices, hash the columns on the GPU, check paths
-int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::PoseidonSponge& sponge, bool* ok) {
+// plain cudaMalloc'ed buffer released at scope exit (the verifier returns early on every failed check)
+struct DevMem {
+  void* p = nullptr;
+  ~DevMem() {
+    if (p) cudaFree(p);
+  }
+  int alloc(Ctx* c, size_t bytes) {
+    LG_CUDA(c, cudaMalloc(&p, bytes ? bytes : 1));
+    return OK;
+  }
+};
+
+// cols_keep (optional): receives the device copy of the t opened columns (t x rows, contiguous) for the per-column checks
+int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::PoseidonSponge& sponge, bool* ok,
+                    DevMem* cols_keep = nullptr) {
   *ok = false;
   const std::vector<uint8_t> seed = sponge.squeeze_bytes(32);
   std::vector<uint64_t> idx(L->t);
@@ -537,7 +551,8 @@ int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::Pose
   int s = hash_column_list(c, dcols, rows, L->t, ddig, L->ctx->col_len_prefix);
   cudaMemcpyAsync(dig.data(), ddig, dig.size(), cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
-  cudaFree(dcols);
+  if (cols_keep) cols_keep->p = dcols;
+  else cudaFree(dcols);
   cudaFree(ddig);
   if (s != OK) return s;
   if (e != cudaSuccess) return set_error(c, ERR_CUDA, cudaGetErrorString(e));
@@ -1417,13 +1432,25 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
   sp.absorb_bytes(P->root.data(), 32);
   // ---- verify_interleaved (671-708)
   std::vector<uint8_t> seed = sp.squeeze_bytes(32);
-  std::vector<Fq> r(rows);
-  LG_TRY(lg_expand_fr(ctx, seed.data(), rows, (uint64_t*)r.data()));
+  cudaSetDevice(c->device);
+  DevMem r_dev, chk;
+  LG_TRY(r_dev.alloc(c, rows * sizeof(Fr)));
+  LG_TRY(chk.alloc(c, L->t * sizeof(Fr)));
+  std::vector<Fq> got(L->t);
+  // every per-column check below is a dot product over an opened column: one CTA per column on the device
+  auto run_checks = [&](int mode, const DevMem& cols, const void* w) -> int {
+    LG_TRY(lg::column_checks(c, mode, (const Fr*)cols.p, (const Fr*)w, rows, L->t, (Fr*)chk.p));
+    LG_CUDA(c, cudaMemcpyAsync(got.data(), chk.p, L->t * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OK;
+  };
+  LG_TRY(expand_fr(c, seed.data(), rows, (Fr*)r_dev.p));
   sp.absorb_field(P->preenc_u_lc);
   bool ok;
-  LG_TRY(verify_openings(L, P->interleaved, P->root, sp, &ok));
-  if (!ok) return OK;
   {
+    DevMem cols;
+    LG_TRY(verify_openings(L, P->interleaved, P->root, sp, &ok, &cols));
+    if (!ok) return OK;
     std::vector<Fq> msg(P->preenc_u_lc);  // reed_solomon_interpolate: msg.resize(k) pads or truncates (998-1002)
     msg.resize(k, lgh::kZero);
     lg_matrix* W = nullptr;
@@ -1432,11 +1459,9 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
     int s = lg_matrix_read_rows(W, 0, 1, (uint64_t*)w.data());
     lg_matrix_free(W);
     if (s != OK) return s;
-    for (size_t q = 0; q < L->t; q++) {
-      Fq acc = lgh::kZero;
-      for (size_t i = 0; i < rows; i++) acc = lgh::add(acc, lgh::mul(r[i], P->interleaved.columns[q][i]));
-      if (w[P->interleaved.leaf_index[q]] != acc) return OK;
-    }
+    LG_TRY(run_checks(0, cols, r_dev.p));  // <r, column> (705-707)
+    for (size_t q = 0; q < L->t; q++)
+      if (w[P->interleaved.leaf_index[q]] != got[q]) return OK;
   }
   // ---- verify_linear (749-830)
   seed = sp.squeeze_bytes(32);
@@ -1475,28 +1500,34 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
   }
   sp.absorb_field(ql);
   {
-    int s = verify_openings(L, P->linear, P->root, sp, &ok);
+    DevMem cols, rcols, idx_dev;
+    int s = verify_openings(L, P->linear, P->root, sp, &ok, &cols);
     if (s != OK || !ok) {
       free_ra();
       return s;
     }
-    std::vector<Fq> rcols(L->t * rows);
-    s = lg_open(RA, P->linear.leaf_index.data(), L->t, (uint64_t*)rcols.data(), nullptr, nullptr);
+    // the same columns of R_A, gathered on the device, then <R_A column, U column> per opened column (822-829)
+    s = rcols.alloc(c, L->t * rows * sizeof(Fr));
+    if (s == OK) s = idx_dev.alloc(c, L->t * sizeof(uint64_t));
+    if (s == OK && cudaMemcpyAsync(idx_dev.p, P->linear.leaf_index.data(), L->t * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                   c->stream) != cudaSuccess)
+      s = fail(ctx, ERR_CUDA, "index upload failed");
+    if (s == OK) s = lg::gather_open(c, RA->m, (const uint64_t*)idx_dev.p, L->t, (Fr*)rcols.p, nullptr, nullptr);
+    if (s == OK) s = run_checks(1, cols, rcols.p);
     free_ra();
     if (s != OK) return s;
     const Fq g = lgh::root_of_unity(log_k + 3);
     for (size_t q = 0; q < L->t; q++) {
       const uint64_t j = P->linear.leaf_index[q];
       const Fq ev = (j % cof == 0) ? ie[j / cof] : poly_eval(ql, lgh::pow_u64(g, j));
-      Fq acc = lgh::kZero;
-      for (size_t i = 0; i < rows; i++) acc = lgh::add(acc, lgh::mul(rcols[q * rows + i], P->linear.columns[q][i]));
-      if (acc != ev) return OK;
+      if (got[q] != ev) return OK;
     }
   }
   // ---- verify_quadratic_constraints (861-933)
   seed = sp.squeeze_bytes(32);
-  std::vector<Fq> rq(m);
-  LG_TRY(lg_expand_fr(ctx, seed.data(), m, (uint64_t*)rq.data()));
+  DevMem rq_dev;
+  LG_TRY(rq_dev.alloc(c, m * sizeof(Fr)));
+  LG_TRY(expand_fr(c, seed.data(), m, (Fr*)rq_dev.p));
   const std::vector<Fq>& qq = P->quadratic_poly;
   const size_t deg_q = qq.empty() ? 0 : qq.size() - 1;
   if (deg_q >= 2 * k - 1) return OK;
@@ -1506,17 +1537,16 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
   for (size_t cc = 0; cc < k; cc++)
     if (!iq[2 * cc].is_zero()) return OK;
   sp.absorb_field(qq);
-  LG_TRY(verify_openings(L, P->quadratic, P->root, sp, &ok));
-  if (!ok) return OK;
   {
+    DevMem cols;
+    LG_TRY(verify_openings(L, P->quadratic, P->root, sp, &ok, &cols));
+    if (!ok) return OK;
+    LG_TRY(run_checks(2, cols, rq_dev.p));  // sum_i r_i (x_i y_i - z_i) per opened column (909-932)
     const Fq g = lgh::root_of_unity(log_k + 3);
     for (size_t q = 0; q < L->t; q++) {
       const uint64_t j = P->quadratic.leaf_index[q];
-      const std::vector<Fq>& col = P->quadratic.columns[q];
       const Fq lhs = (j % cof == 0) ? iq[j / cof] : poly_eval(qq, lgh::pow_u64(g, j));
-      Fq rhs = lgh::kZero;
-      for (size_t i = 0; i < m; i++) rhs = lgh::add(rhs, lgh::mul(rq[i], lgh::sub(lgh::mul(col[i], col[i + m]), col[i + 2 * m])));
-      if (lhs != rhs) return OK;
+      if (lhs != got[q]) return OK;
     }
   }
   *accepted = 1;

@@ -160,6 +160,9 @@ int spmv_right_block(Ctx* ctx, const uint32_t* col_ptr, const uint32_t* row_idx,
                      const Fr* r, size_t mk, Fr* out);
 struct Matrix;
 int gather_open(Ctx* ctx, const Matrix& m, const uint64_t* idx_dev, size_t t, Fr* cols_dev, uint8_t* sib_dev, uint8_t* auth_dev);
+// verifier's per-column checks on t opened columns (t x rows contiguous, Montgomery); mode 0/1/2 = interleaved / linear /
+// quadratic (protocol.cu); out: t elements
+int column_checks(Ctx* ctx, int mode, const Fr* cols, const Fr* w, size_t rows, size_t t, Fr* out);
 // batched inverse NTT of `rows` rows of length 2^log_k, natural order in and out, includes 1/k
 int intt_rows(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int log_k);
 // column hashing (a4+a5): leaves[j] = BLAKE2s(u64le(R) || canonical LE bytes of column j)

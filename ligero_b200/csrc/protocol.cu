@@ -343,8 +343,52 @@ int gather_open(Ctx* ctx, const Matrix& m, const uint64_t* idx_dev, size_t t, Fr
   int log_n = 0;
   while (((size_t)1 << log_n) < m.n) log_n++;
   gather_columns_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(m.u, m.rows, m.log_k, m.rho_inv, idx_dev, t, cols_dev);
-  gather_paths_kernel<<<(unsigned)((t + 63) / 64), 64, 0, ctx->stream>>>(m.leaves, m.nodes, m.n, log_n, idx_dev, t, sib_dev, auth_dev);
-  ctx->launches += 2;
+  ctx->launches++;
+  if (sib_dev && auth_dev) {  // columns only: the verifier's gather from its own re-encoded matrix
+    gather_paths_kernel<<<(unsigned)((t + 63) / 64), 64, 0, ctx->stream>>>(m.leaves, m.nodes, m.n, log_n, idx_dev, t, sib_dev, auth_dev);
+    ctx->launches++;
+  }
+  LG_CUDA(ctx, cudaGetLastError());
+  return OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The verifier's per-column checks (src/ligero/mod.rs:705-707, 822-829, 909-932) for t opened columns held as
+// t x rows contiguous Montgomery elements: one CTA per column, partial sums per thread, tree reduction in shared memory.
+//   MODE 0: out[q] = sum_i w[i] * col_q[i]                                   (Test-Interleaved, w = r)
+//   MODE 1: out[q] = sum_i w[q*rows + i] * col_q[i]                          (Test-Linear, w = the same columns of R_A)
+//   MODE 2: out[q] = sum_{i<m} w[i] * (col_q[i] * col_q[m+i] - col_q[2m+i])  (Test-Quadratic, rows = 4m)
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) column_check_kernel(const Fr* __restrict__ cols, const Fr* __restrict__ w, size_t rows,
+                                                           Fr* __restrict__ out) {
+  __shared__ Fr part[256];
+  const size_t q = blockIdx.x;
+  const Fr* col = cols + q * rows;
+  const size_t count = MODE == 2 ? rows / 4 : rows;
+  Fr acc = fr_zero();
+  for (size_t i = threadIdx.x; i < count; i += blockDim.x) {
+    Fr term;
+    if (MODE == 0) term = fr_mul(p_ld(w + i), p_ld(col + i));
+    else if (MODE == 1) term = fr_mul(p_ld(w + q * rows + i), p_ld(col + i));
+    else term = fr_mul(p_ld(w + i), fr_sub(fr_mul(p_ld(col + i), p_ld(col + count + i)), p_ld(col + 2 * count + i)));
+    acc = fr_add(acc, term);
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) part[threadIdx.x] = fr_add(part[threadIdx.x], part[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p_st(out + q, part[0]);
+}
+
+int column_checks(Ctx* ctx, int mode, const Fr* cols, const Fr* w, size_t rows, size_t t, Fr* out) {
+  if (t == 0) return OK;
+  if (mode == 0) column_check_kernel<0><<<(unsigned)t, 256, 0, ctx->stream>>>(cols, w, rows, out);
+  else if (mode == 1) column_check_kernel<1><<<(unsigned)t, 256, 0, ctx->stream>>>(cols, w, rows, out);
+  else column_check_kernel<2><<<(unsigned)t, 256, 0, ctx->stream>>>(cols, w, rows, out);
+  ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
 }
