@@ -409,6 +409,13 @@ class ShardedProver:
         loc = full.view(self.rows, self.k, 4)[self.row_ids.to(full.device)].reshape(-1, 4).contiguous()
         return loc.to(self.committer.dev)
 
+    def prove(self, var_assignment, sponge):
+        """LigeroCircuit::prove over G GPUs from the variable assignment alone: every rank runs the (cheap, replicated)
+        evaluation trace on its own GPU (lg_ligero_witness_matrix_dev), keeps its rows of [X;Y;Z;W] and goes on with
+        prove_matrix -- no host trace, no matrix upload."""
+        pre = self.L.witness_matrix_device(var_assignment)
+        return self.prove_matrix(self.local_rows(pre), sponge)
+
     # -- collectives over host-sized results -------------------------------------------------------
     def _gather(self, part_np):
         import numpy as np

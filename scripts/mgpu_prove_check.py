@@ -68,6 +68,9 @@ def main():
         dt = time.perf_counter() - t0
         blob = proof.to_bytes()
         accepted = L.verify(proof, lb.PoseidonSponge.test_sponge())
+        # the same from the assignment alone: replicated device trace, local rows, sharded commit and tests
+        blob_dev = sp.prove(assignment, lb.PoseidonSponge.test_sponge()).to_bytes()
+        accepted = accepted and blob_dev == blob
         same = True
         if rank == 0:
             t0 = time.perf_counter()
