@@ -160,10 +160,10 @@ constexpr int kHashStateWords = 18;
 template <bool PREFIX, bool FMA>
 __global__ void __launch_bounds__(64) hash_columns_kernel(const Fr* __restrict__ u, size_t rows, int log_k, int rho,
                                                           size_t row0, size_t row_end, uint32_t* __restrict__ state,
-                                                          uint8_t* __restrict__ leaves) {
-  const size_t pc = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // physical column = plane * k + c
+                                                          uint8_t* __restrict__ leaves, size_t col0, size_t col1) {
+  const size_t pc = col0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // physical column = plane * k + c
   const size_t k = (size_t)1 << log_k, ncols = (size_t)rho * k;
-  if (pc >= ncols) return;
+  if (pc >= col1) return;
   const size_t s = pc >> log_k, c = pc & (k - 1);
   const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
   const uint64_t nblocks = total == 0 ? 1 : (total + 63) / 64;
@@ -302,12 +302,12 @@ template <bool PREFIX>
 __global__ void __launch_bounds__(32 * kQuadWarps) hash_columns_quad_kernel(const Fr* __restrict__ u, size_t rows, int log_k,
                                                                             int rho, size_t row0, size_t row_end,
                                                                             uint32_t* __restrict__ state,
-                                                                            uint8_t* __restrict__ leaves) {
+                                                                            uint8_t* __restrict__ leaves, size_t col0, size_t col1) {
   __shared__ __align__(16) uint32_t sm[kQuadWarps * 8 * kQuadColWords];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t k = (size_t)1 << log_k, ncols = (size_t)rho * k;
-  const size_t pc0 = ((size_t)blockIdx.x * kQuadWarps + warp) * 8;  // first of this warp's 8 physical columns
-  if (pc0 >= ncols) return;                                           // whole warps only (k is a multiple of 8)
+  const size_t pc0 = col0 + ((size_t)blockIdx.x * kQuadWarps + warp) * 8;  // first of this warp's 8 physical columns
+  if (pc0 >= col1) return;  // whole warps only (k, col0 and col1 are multiples of 8)
   const size_t s = pc0 >> log_k, c0 = pc0 & (k - 1);
   const Fr* base = u + s * rows * k + c0;
   const uint64_t total = (PREFIX ? 8ull : 0ull) + 32ull * rows;
@@ -405,29 +405,46 @@ __global__ void __launch_bounds__(32 * kQuadWarps) hash_columns_quad_kernel(cons
   dst[4 + i] = h_hi;
 }
 
+static void launch_quad(cudaStream_t st, const Fr* u, size_t rows, int log_k, int rho_inv, size_t row0, size_t row_end,
+                        uint32_t* state, uint8_t* leaves, bool len_prefix, size_t col0, size_t col1) {
+  const unsigned grid = (unsigned)(((col1 - col0) / 8 + kQuadWarps - 1) / kQuadWarps), bs = 32 * kQuadWarps;
+  if (len_prefix) hash_columns_quad_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves, col0, col1);
+  else hash_columns_quad_kernel<false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves, col0, col1);
+}
+
+static void launch_thread(cudaStream_t st, const Fr* u, size_t rows, int log_k, int rho_inv, size_t row0, size_t row_end,
+                          uint32_t* state, uint8_t* leaves, bool len_prefix, bool fma, size_t col0, size_t col1) {
+  const unsigned bs = 64;
+  const unsigned grid = (unsigned)((col1 - col0 + bs - 1) / bs);
+  if (len_prefix && fma)
+    hash_columns_kernel<true, true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves, col0, col1);
+  else if (len_prefix)
+    hash_columns_kernel<true, false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves, col0, col1);
+  else if (fma)
+    hash_columns_kernel<false, true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves, col0, col1);
+  else
+    hash_columns_kernel<false, false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves, col0, col1);
+}
+
 int hash_columns_range(Ctx* ctx, cudaStream_t st, const Fr* u, size_t rows, int log_k, int rho_inv, size_t row0,
                        size_t row_end, uint32_t* state, uint8_t* leaves, bool len_prefix) {
   if (row0 >= row_end || row_end > rows || ((row0 > 0 || row_end < rows) && !state))
     return set_error(ctx, ERR_INVALID, "column hashing tile out of range, or a partial tile without a state buffer");
   const size_t n = (size_t)rho_inv << log_k;
   if (log_k >= 3 && n <= ctx->hash_quad_max) {
-    const unsigned grid = (unsigned)((n / 8 + kQuadWarps - 1) / kQuadWarps), bs = 32 * kQuadWarps;
-    if (len_prefix) hash_columns_quad_kernel<true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
-    else hash_columns_quad_kernel<false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+    launch_quad(st, u, rows, log_k, rho_inv, row0, row_end, state, leaves, len_prefix, 0, n);
     ctx->launches++;
     LG_CUDA(ctx, cudaGetLastError());
     return OK;
   }
-  const unsigned bs = 64;
-  const unsigned grid = (unsigned)((n + bs - 1) / bs);
   // at most one warp per SM sub-partition: the warp is bound by its own dependent chain and instruction count, so
   // plain additions win (8.16 against 9.52 ms at 16 384 columns x 16 388 rows); with more warps the ALU pipe is the
   // bound and the additions belong on the FMA pipe (26.5 against 30.0 ms at 65 536 columns)
   const bool fma = n > (size_t)128 * ctx->sm_count;
-  if (len_prefix && fma) hash_columns_kernel<true, true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
-  else if (len_prefix) hash_columns_kernel<true, false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
-  else if (fma) hash_columns_kernel<false, true><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
-  else hash_columns_kernel<false, false><<<grid, bs, 0, st>>>(u, rows, log_k, rho_inv, row0, row_end, state, leaves);
+  // (Measured and dropped: giving the thread-per-column kernel a whole number of warps per sub-partition, 3 x 592 x 32 =
+  // 56 832 of 65 536 columns, and hashing the other 8 704 four lanes per column on a second stream.  The four-lane
+  // chains starve next to warps that saturate the ALU pipe: 37.8 ms against 26.5 ms.)
+  launch_thread(st, u, rows, log_k, rho_inv, row0, row_end, state, leaves, len_prefix, fma, 0, n);
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
