@@ -200,12 +200,6 @@ void host_fft(std::vector<Fq>& a, bool inverse) {
   }
 }
 
-Fq poly_eval(const std::vector<Fq>& c, const Fq& x) {
-  Fq acc = lgh::kZero;
-  for (size_t i = c.size(); i-- > 0;) acc = lgh::add(lgh::mul(acc, x), c[i]);
-  return acc;
-}
-
 // ---- constraint matrix (right-hand block of A) straight into CSC ------------------------------------
 struct Triplet {
   uint32_t col, row, vid;
@@ -1429,6 +1423,15 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
   const size_t m = L->m, k = L->k, n = L->n, rows = 4 * m;
   int log_k = 0;
   while (((size_t)1 << log_k) < k) log_k++;
+  const bool vt = getenv("LG_VERIFY_TIMING") != nullptr;
+  auto vt0 = std::chrono::steady_clock::now();
+  auto vlap = [&](const char* what) {
+    if (!vt) return;
+    cudaStreamSynchronize(c->stream);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[lg_verify] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - vt0).count());
+    vt0 = now;
+  };
   sp.absorb_bytes(P->root.data(), 32);
   // ---- verify_interleaved (671-708)
   std::vector<uint8_t> seed = sp.squeeze_bytes(32);
@@ -1444,13 +1447,25 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
     LG_CUDA(c, cudaStreamSynchronize(c->stream));
     return OK;
   };
+  // a test polynomial (degree < 2k - 1) on the whole n-point domain from its values on the 2k-point domain: one
+  // device encode of a single row of length 2k at rate 2k/n (the opened indices are spread over all cosets)
+  auto on_large_domain = [&](const std::vector<Fq>& evals_2k, std::vector<Fq>& out_n) -> int {
+    lg_matrix* Q = nullptr;
+    LG_TRY(lg_encode(ctx, (const uint64_t*)evals_2k.data(), 1, 2 * k, (uint32_t)(n / (2 * k)), &Q));
+    out_n.resize(n);
+    const int s = lg_matrix_read_rows(Q, 0, 1, (uint64_t*)out_n.data());
+    lg_matrix_free(Q);
+    return s;
+  };
   LG_TRY(expand_fr(c, seed.data(), rows, (Fr*)r_dev.p));
   sp.absorb_field(P->preenc_u_lc);
   bool ok;
   {
     DevMem cols;
+    vlap("expand r + absorb lc");
     LG_TRY(verify_openings(L, P->interleaved, P->root, sp, &ok, &cols));
     if (!ok) return OK;
+    vlap("openings (interleaved)");
     std::vector<Fq> msg(P->preenc_u_lc);  // reed_solomon_interpolate: msg.resize(k) pads or truncates (998-1002)
     msg.resize(k, lgh::kZero);
     lg_matrix* W = nullptr;
@@ -1462,6 +1477,7 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
     LG_TRY(run_checks(0, cols, r_dev.p));  // <r, column> (705-707)
     for (size_t q = 0; q < L->t; q++)
       if (w[P->interleaved.leaf_index[q]] != got[q]) return OK;
+    vlap("encode lc + checks");
   }
   // ---- verify_linear (749-830)
   seed = sp.squeeze_bytes(32);
@@ -1475,6 +1491,7 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
     cudaStreamSynchronize(c->stream);
     cudaFree(ra);
     if (s != OK) return s;
+    vlap("r_a + full-rate encode");
   }
   auto free_ra = [&]() {
     if (RA) lg_matrix_free(RA);
@@ -1489,7 +1506,6 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
   std::vector<Fq> ie(ql);
   ie.resize(2 * k, lgh::kZero);
   host_fft(ie, false);
-  const size_t cof = n / (2 * k);
   {
     Fq sum = lgh::kZero;
     for (size_t i = 0; i < 2 * k; i += 2) sum = lgh::add(sum, ie[i]);
@@ -1499,6 +1515,7 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
     }
   }
   sp.absorb_field(ql);
+  vlap("host fft + absorb linear");
   {
     DevMem cols, rcols, idx_dev;
     int s = verify_openings(L, P->linear, P->root, sp, &ok, &cols);
@@ -1514,14 +1531,14 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
       s = fail(ctx, ERR_CUDA, "index upload failed");
     if (s == OK) s = lg::gather_open(c, RA->m, (const uint64_t*)idx_dev.p, L->t, (Fr*)rcols.p, nullptr, nullptr);
     if (s == OK) s = run_checks(1, cols, rcols.p);
+    vlap("openings + checks (linear)");
     free_ra();
+    vlap("free R_A");
     if (s != OK) return s;
-    const Fq g = lgh::root_of_unity(log_k + 3);
-    for (size_t q = 0; q < L->t; q++) {
-      const uint64_t j = P->linear.leaf_index[q];
-      const Fq ev = (j % cof == 0) ? ie[j / cof] : poly_eval(ql, lgh::pow_u64(g, j));
-      if (got[q] != ev) return OK;
-    }
+    std::vector<Fq> q_n;
+    LG_TRY(on_large_domain(ie, q_n));
+    for (size_t q = 0; q < L->t; q++)
+      if (got[q] != q_n[P->linear.leaf_index[q]]) return OK;
   }
   // ---- verify_quadratic_constraints (861-933)
   seed = sp.squeeze_bytes(32);
@@ -1542,12 +1559,11 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
     LG_TRY(verify_openings(L, P->quadratic, P->root, sp, &ok, &cols));
     if (!ok) return OK;
     LG_TRY(run_checks(2, cols, rq_dev.p));  // sum_i r_i (x_i y_i - z_i) per opened column (909-932)
-    const Fq g = lgh::root_of_unity(log_k + 3);
-    for (size_t q = 0; q < L->t; q++) {
-      const uint64_t j = P->quadratic.leaf_index[q];
-      const Fq lhs = (j % cof == 0) ? iq[j / cof] : poly_eval(qq, lgh::pow_u64(g, j));
-      if (lhs != got[q]) return OK;
-    }
+    vlap("quadratic: fft, absorb, openings, checks");
+    std::vector<Fq> q_n;
+    LG_TRY(on_large_domain(iq, q_n));
+    for (size_t q = 0; q < L->t; q++)
+      if (q_n[P->quadratic.leaf_index[q]] != got[q]) return OK;
   }
   *accepted = 1;
   return OK;
