@@ -214,9 +214,10 @@ int lg_circuit_mul(lg_circuit* c, size_t left, size_t right, size_t* index_out);
 int lg_circuit_counts(const lg_circuit* c, size_t* nodes, size_t* constants, size_t* variables, size_t* gates); /* 38-63 */
 /* node inspection: type 0 = Variable, 1 = Constant, 2 = Add, 3 = Mul */
 int lg_circuit_node(const lg_circuit* c, size_t index, int* type, size_t* left, size_t* right, uint64_t value[4]);
-/* evaluate_multioutput, 325-400: out_vals = Fr[n_outputs] values of the output nodes */
+/* evaluate_multioutput, 325-400: out_vals (capacity Fr[n_outputs]) receives the values of the DISTINCT output nodes in
+ * node-index order, as the reference's filter over the trace yields them; *n_values_out (nullable) = how many */
 int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
-                        size_t n_outputs, uint64_t* out_vals);
+                        size_t n_outputs, uint64_t* out_vals, size_t* n_values_out);
 /* from_constraint_system, 455-520.  A, B, C as ConstraintSystem::to_matrices yields them, in CSR form:
  * row_ptr[i][n_constraints+1], col_idx[i][nnz], coeffs[i] = Fr[nnz]; column 0 is the constant one and
  * n_cols = num_instance_variables + num_witness_variables.  outputs: size_t[n_constraints]. */

@@ -95,7 +95,7 @@ SIGNATURES = {
     "lg_circuit_mul": (c_int, [c_void_p, c_size_t, c_size_t, POINTER(c_size_t)]),
     "lg_circuit_counts": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
     "lg_circuit_node": (c_int, [c_void_p, c_size_t, POINTER(c_int), POINTER(c_size_t), POINTER(c_size_t), c_void_p]),
-    "lg_circuit_evaluate": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "lg_circuit_evaluate": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "lg_circuit_from_r1cs": (c_int, [c_size_t, c_size_t, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                      POINTER(c_void_p), c_void_p]),
     "lg_sponge_new": (c_int, [c_int, c_int, c_uint64, c_void_p, c_void_p, c_int, c_int, POINTER(c_void_p)]),

@@ -172,10 +172,11 @@ class ArithmeticCircuit:
         idx = np.array([i for i, _ in vars], dtype=np.uint64)
         vals = fr_to_limbs([v for _, v in vars])
         outs = np.array(list(outputs), dtype=np.uint64)
-        res = np.zeros((len(outs), 4), dtype=np.uint64)
-        self._check(self.lib.lg_circuit_evaluate(self.handle, _ptr(idx), _ptr(vals), len(idx), _ptr(outs), len(outs), _ptr(res)),
-                    "evaluate")
-        return limbs_to_fr(res)
+        res = np.zeros((max(len(outs), 1), 4), dtype=np.uint64)
+        count = c_size_t()
+        self._check(self.lib.lg_circuit_evaluate(self.handle, _ptr(idx), _ptr(vals), len(idx), _ptr(outs), len(outs), _ptr(res),
+                                                 byref(count)), "evaluate")
+        return limbs_to_fr(res[: count.value])      # node order, one value per distinct output (mod.rs:384-389)
 
     def evaluate_node(self, vars, node: int) -> int:
         return self.evaluate_multioutput(vars, [node])[0]

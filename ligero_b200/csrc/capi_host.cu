@@ -761,7 +761,7 @@ int lg_circuit_node(const lg_circuit* c, size_t index, int* type, size_t* left, 
 
 // evaluation_trace_multioutput + evaluate_multioutput (mod.rs:325-400): values of the output nodes
 int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
-                        size_t n_outputs, uint64_t* out_vals) {
+                        size_t n_outputs, uint64_t* out_vals, size_t* n_values_out) {
   if (!c || (n_vars && (!var_idx || !var_vals)) || !outputs || !out_vals) return ERR_INVALID;
   std::vector<std::pair<size_t, Fq>> vars(n_vars);
   for (size_t i = 0; i < n_vars; i++) {
@@ -777,7 +777,13 @@ int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64
     const_cast<lg_circuit*>(c)->error = err;
     return s;
   }
-  for (size_t i = 0; i < n_outputs; i++) memcpy(out_vals + 4 * i, vals[outputs[i]].l, 32);
+  // the reference filters the trace by membership in `outputs` (mod.rs:384-389): values come in NODE order, one per
+  // distinct output node
+  std::vector<size_t> sorted(outs);
+  std::sort(sorted.begin(), sorted.end());
+  sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+  for (size_t i = 0; i < sorted.size(); i++) memcpy(out_vals + 4 * i, vals[sorted[i]].l, 32);
+  if (n_values_out) *n_values_out = sorted.size();
   return OK;
 }
 
