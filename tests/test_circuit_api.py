@@ -162,3 +162,39 @@ def test_random_builder_programs_equal_the_oracle():
         assign = [(v, rnd.randrange(P)) for v in vars_]
         outs = [nodes[-1], rnd.choice(nodes)]
         assert c.evaluate_multioutput(assign, outs) == oc.evaluate_multioutput(assign, outs)
+
+
+def _same_nodes(c, oc):
+    assert c.num_nodes() == oc.num_nodes() and c.num_constants() == oc.num_constants() and c.num_gates() == oc.num_gates()
+    for idx in range(c.num_nodes()):
+        nd, on = c.node(idx), oc.nodes[idx]
+        if nd[0] == "const":
+            assert on[0] == O.CONST and on[1] == nd[1], idx
+        elif nd[0] == "var":
+            assert on[0] == O.VAR, idx
+        else:
+            assert on[0] == (O.ADD if nd[0] == "add" else O.MUL) and (on[1], on[2]) == (nd[1], nd[2]), idx
+
+
+def test_from_constraint_system_equals_the_oracle():
+    """from_constraint_system (src/arithmetic_circuit/mod.rs:455-520) on the circom fixtures, the cube system of the
+    reference's tests (15 nodes, tests.rs:239) and the hand-built repeated-squaring system: same circuit as the oracle's"""
+    from tests.golden_util import load_r1cs
+    from tests.util import repeated_squaring_r1cs
+    systems = []
+    for name in ("multiplication", "poseidon"):
+        a, b, c, nw, wit = load_r1cs(name)
+        systems.append((a, b, c, nw, wit))
+    systems.append(([[(P - 1, 1)], [(1, 1)]], [[(1, 1)], [(1, 2)]], [[(P - 1, 2)], [(27, 0)]], 3, [1, 3, 9]))
+    systems.append(repeated_squaring_r1cs(10, 3))
+    for a, b, c, nw, wit in systems:
+        circ, outs = lb.ArithmeticCircuit.from_constraint_system(a, b, c, nw)
+        oc, oouts = O.ArithmeticCircuit.from_constraint_system(a, b, c, nw)
+        assert outs == oouts
+        _same_nodes(circ, oc)
+        va = list(enumerate(wit))[1:]
+        assert circ.evaluate_multioutput(va, outs) == oc.evaluate_multioutput(va, oouts) == [1] * len(outs)
+    circ, _ = lb.ArithmeticCircuit.from_constraint_system(*systems[2][:4])
+    assert circ.num_nodes() == 15
+    with pytest.raises(lb.LigeroB200Error):                      # an empty row: add_nodes(empty).unwrap() panics (148-153)
+        lb.ArithmeticCircuit.from_constraint_system([[]], [[(1, 1)]], [[(1, 1)]], 2)
