@@ -561,33 +561,53 @@ int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::Pose
 }
 
 // ---- serialisation (arkworks CanonicalSerialize-compatible layout; the reference defines none) -------
-void put_u64(std::vector<uint8_t>& b, uint64_t v) {
-  for (int i = 0; i < 8; i++) b.push_back((uint8_t)(v >> (8 * i)));
-}
-void put_fr(std::vector<uint8_t>& b, const Fq& x) {
-  const Fq c = lgh::from_mont(x);
-  const uint8_t* p = (const uint8_t*)c.l;
-  b.insert(b.end(), p, p + 32);
-}
-void put_frs(std::vector<uint8_t>& b, const std::vector<Fq>& v) {
-  put_u64(b, v.size());
-  for (auto& x : v) put_fr(b, x);
-}
-void put_digest(std::vector<uint8_t>& b, const Digest& d) {
-  put_u64(b, 32);
-  b.insert(b.end(), d.begin(), d.end());
-}
-void put_opened(std::vector<uint8_t>& b, const Opened& o) {
-  put_u64(b, o.columns.size());
-  for (auto& col : o.columns) put_frs(b, col);
-  put_u64(b, o.leaf_index.size());
-  for (size_t q = 0; q < o.leaf_index.size(); q++) {  // Path { leaf_sibling_hash, auth_path, leaf_index }
-    put_digest(b, o.sibling[q]);
-    put_u64(b, o.auth[q].size());
-    for (auto& d : o.auth[q]) put_digest(b, d);
-    put_u64(b, o.leaf_index[q]);
+// writes into the caller's buffer, or only counts when there is none (one code path for the size query and the copy:
+// a 2^24-gate proof is 247 MB)
+struct Writer {
+  uint8_t* p;
+  size_t cap, pos = 0;
+  bool ok = true;
+  Writer(uint8_t* buf, size_t capacity) : p(buf), cap(capacity) {}
+  void raw(const void* src, size_t n) {
+    if (p) {
+      if (pos + n > cap) ok = false;
+      else memcpy(p + pos, src, n);
+    }
+    pos += n;
   }
-}
+  void u64(uint64_t v) { raw(&v, 8); }  // little endian host
+  void fr(const Fq& x) {
+    if (p) {
+      const Fq c = lgh::from_mont(x);
+      raw(c.l, 32);
+    } else {
+      pos += 32;
+    }
+  }
+  void frs(const std::vector<Fq>& v) {
+    u64(v.size());
+    if (!p) {
+      pos += 32 * v.size();
+      return;
+    }
+    for (auto& x : v) fr(x);
+  }
+  void digest(const Digest& d) {
+    u64(32);
+    raw(d.data(), 32);
+  }
+  void opened(const Opened& o) {
+    u64(o.columns.size());
+    for (auto& col : o.columns) frs(col);
+    u64(o.leaf_index.size());
+    for (size_t q = 0; q < o.leaf_index.size(); q++) {  // Path { leaf_sibling_hash, auth_path, leaf_index }
+      digest(o.sibling[q]);
+      u64(o.auth[q].size());
+      for (auto& d : o.auth[q]) digest(d);
+      u64(o.leaf_index[q]);
+    }
+  }
+};
 struct Reader {
   const uint8_t* p;
   size_t len, pos = 0;
@@ -1628,20 +1648,16 @@ int lg_proof_free(lg_proof* p) {
 }
 int lg_proof_serialize(const lg_proof* P, uint8_t* buf, size_t cap, size_t* len_out) {
   if (!P || !len_out) return ERR_INVALID;
-  std::vector<uint8_t> b;
-  put_digest(b, P->root);
-  put_frs(b, P->preenc_u_lc);
-  put_opened(b, P->interleaved);
-  put_frs(b, P->linear_poly);
-  put_opened(b, P->linear);
-  put_frs(b, P->quadratic_poly);
-  put_opened(b, P->quadratic);
-  *len_out = b.size();
-  if (buf) {
-    if (cap < b.size()) return ERR_INVALID;
-    memcpy(buf, b.data(), b.size());
-  }
-  return OK;
+  Writer w(buf, cap);
+  w.digest(P->root);
+  w.frs(P->preenc_u_lc);
+  w.opened(P->interleaved);
+  w.frs(P->linear_poly);
+  w.opened(P->linear);
+  w.frs(P->quadratic_poly);
+  w.opened(P->quadratic);
+  *len_out = w.pos;
+  return w.ok ? OK : ERR_INVALID;  // buffer too small
 }
 int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out) {
   if (!buf || !out) return ERR_INVALID;
