@@ -66,7 +66,12 @@ def ncu_traffic(kernel: str, R: int, k: int):
             if not (name.endswith(".jsonl") and "ncu_full" in name):
                 continue
             for line in open(os.path.join(pdir, name)):
-                rec = json.loads(line)
+                if not line.startswith("{"):
+                    continue                      # header comments of a summary file
+                try:
+                    rec = json.loads(line)
+                except ValueError:
+                    continue
                 t = rec.get("dram_traffic_bytes")
                 if kernel in rec.get("kernel", "") and t == t and t:
                     best = float(t)          # later files (later rounds / captures) win
