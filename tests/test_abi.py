@@ -51,3 +51,17 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), f"{os.path.join(dirpath, f)} references the oracle"
+
+
+def test_nothing_at_run_time_reads_the_reference_tree():
+    """/root/reference does not exist on the GPU box: the product, the GPU tests, the scripts, smoke() and bench.py must
+    not name it (the fixture generator and the CPU-only reference-facts test, which skips without it, may)."""
+    import glob
+    files = [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py"), os.path.join(ROOT, "tests", "util.py")]
+    files += glob.glob(os.path.join(ROOT, "tests", "test_gpu_*.py"))
+    for top in ("ligero_b200", "scripts"):
+        for dirpath, _, names in os.walk(os.path.join(ROOT, top)):
+            files += [os.path.join(dirpath, f) for f in names if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp", ".sh", ".inc"))]
+    assert len(files) > 30
+    for p in files:
+        assert "/root/reference" not in open(p).read(), f"{p} names /root/reference"
