@@ -477,6 +477,7 @@ int lg_ctx_destroy(lg_ctx* ctx) {
   cudaStreamSynchronize(ctx->c.stream);
   for (auto& kv : ctx->c.tables) {
     cudaFree(kv.second.w_fwd);  // w_inv and scale live in the same allocation
+    if (kv.second.scale4) cudaFree(kv.second.scale4);
   }
   if (ctx->c.scratch) cudaFree(ctx->c.scratch);
   if (ctx->c.copy_stream) {

@@ -114,6 +114,44 @@ __device__ __forceinline__ Fr fr_mul_shoup_ld(const Fr& y, const FrTw* __restric
 }
 #endif
 
+#ifdef __CUDACC__
+// The same product with the table entry split into four 16-byte pieces (structure of arrays): consecutive lanes
+// reading consecutive entries touch consecutive 16-byte slots, so a warp's read of one piece is four full wavefronts
+// of shared memory (or four full sectors of global memory) instead of 32 scattered 64-byte entries.
+//   shared-memory twiddles (persistent encoder): 32-bit shared addresses of {w.lo, w.hi, p.lo, p.hi}
+__device__ __forceinline__ Fr fr_mul_shoup_sm(const Fr& y, uint32_t a_wlo, uint32_t a_whi, uint32_t a_plo, uint32_t a_phi) {
+  const uint32_t y0 = y.v[0], y1 = y.v[1], y2 = y.v[2], y3 = y.v[3], y4 = y.v[4], y5 = y.v[5], y6 = y.v[6], y7 = y.v[7];
+  uint32_t p0, p1, p2, p3, p4, p5, p6, p7;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p0), "=r"(p1), "=r"(p2), "=r"(p3) : "r"(a_plo));
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p4), "=r"(p5), "=r"(p6), "=r"(p7) : "r"(a_phi));
+#include "fr_shoup_body_q.inc"
+  uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(a_wlo));
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "r"(a_whi));
+#include "fr_shoup_body_t.inc"
+  (void)hx; (void)he6;
+  Fr t;
+  t.v[0] = e0; t.v[1] = e1; t.v[2] = e2; t.v[3] = e3; t.v[4] = e4; t.v[5] = e5; t.v[6] = e6; t.v[7] = e7;
+  return t;
+}
+//   global SoA table (coset scale factors): piece pointers `stride` uint4 apart in the order w.lo, w.hi, p.lo, p.hi
+__device__ __forceinline__ Fr fr_mul_shoup_g4(const Fr& y, const uint4* __restrict__ tp, uint32_t stride) {
+  const uint32_t y0 = y.v[0], y1 = y.v[1], y2 = y.v[2], y3 = y.v[3], y4 = y.v[4], y5 = y.v[5], y6 = y.v[6], y7 = y.v[7];
+  uint32_t p0, p1, p2, p3, p4, p5, p6, p7;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p0), "=r"(p1), "=r"(p2), "=r"(p3) : "l"(tp + 2 * stride));
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(p4), "=r"(p5), "=r"(p6), "=r"(p7) : "l"(tp + 3 * stride));
+#include "fr_shoup_body_q.inc"
+  uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "l"(tp));
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "l"(tp + stride));
+#include "fr_shoup_body_t.inc"
+  (void)hx; (void)he6;
+  Fr t;
+  t.v[0] = e0; t.v[1] = e1; t.v[2] = e2; t.v[3] = e3; t.v[4] = e4; t.v[5] = e5; t.v[6] = e6; t.v[7] = e7;
+  return t;
+}
+#endif
+
 // plain 256-bit add (callers guarantee no overflow)
 LG_HD Fr lz_add(const Fr& a, const Fr& b) {
   Fr r;

@@ -45,6 +45,10 @@ struct NttTables {
   FrTw* w_fwd = nullptr;   // omega_k^i,  i < max(1, k/2)
   FrTw* w_inv = nullptr;   // omega_k^-i
   FrTw* scale = nullptr;   // (rho_inv-1) tables of k: scale[(s-1)*k + pos] = g^(s*bitrev(pos)) / k,  g = omega_{rho_inv*k}
+  // the same scale factors for the persistent encoder (log_k >= 10): per coset and per 1024-element chunk four planes of
+  // 1024 16-byte pieces {w.lo, w.hi, p.lo, p.hi}; the entry of chunk position 4t+e sits in slot e*256+t, so the 256 threads
+  // of a group read consecutive slots (own allocation)
+  uint4* scale4 = nullptr;
   FrTw kinv;               // 1/k
 };
 

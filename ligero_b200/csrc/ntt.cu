@@ -162,6 +162,7 @@ struct LocalArgs {
   const FrTw* w_fwd;    // order-2^l tables (compact: every local stage indexes a dense 2^(l-1)-entry array)
   const FrTw* w_inv;
   const FrTw* scale;
+  const uint4* scale4;  // ntt_persist_kernel: SoA copy of `scale` (NttTables::scale4)
   FrTw kinv;            // MODE 1: 1/k
   int final;            // MODE 0: the coset values leaving this kernel are finished codeword elements (q == l)
   int mapped;           // MODE 0: 1 = finished elements (and the plane-0 copy) go through `map`
@@ -333,6 +334,215 @@ __global__ void __launch_bounds__(128, 3) ntt_global_pass_mapped_kernel(const Fr
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent shared-memory encoder for rows of >= 1024 elements (the MODE 0 work of ntt_local_kernel).
+//
+// One CTA per SM, GROUPS independent groups of 256 threads (8 warps), each walking 1024-element chunks with its own
+// named barrier and its own 64 KiB of shared memory (coefficients A, working copy B, two 16-byte half planes each).
+// What the one-CTA-per-chunk kernel paid per product and this one does not:
+//   * twiddles come from ONE shared-memory copy of the order-1024 table per SM (513 entries as four 16-byte planes,
+//     XOR-swizzled: every access pattern of the five radix-4 passes is conflict free) instead of four scattered
+//     64-byte global loads per product through a 32 KiB L1 -- the late passes were bound by the LSU, not the multiplier;
+//     the inverse transform reads the same table backwards: omega^-i = -omega^(512-i), (X-Y) omega^-i = (Y-X) omega^(512-i);
+//   * the data swizzle is conflict free for radix-4 (the radix-8 swizzle of ntt_local_kernel is 2-way conflicted in
+//     the pass over stages 2,3);
+//   * the first inverse pass takes its four elements straight from global memory and the last forward pass stores its
+//     four finished elements straight to global memory (both coalesced: the elements of thread t are t + 256 e), saving
+//     one shared-memory round trip and one barrier per transform;
+//   * the coset scale factors are read from the SoA copy (NttTables::scale4), consecutive lanes -> consecutive slots;
+//   * unit twiddles are skipped only where the whole warp skips (stages 0 and half of stage 1): per-lane skipping in the
+//     later passes made every warp execute both sides of the branch.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLogPE = 10;
+constexpr int kPE = 1 << kLogPE;   // elements per chunk
+constexpr int kPT = kPE / 4;       // threads per group
+constexpr int kTwSlots = 520;      // 513 twiddles, padded
+constexpr size_t kPersistTwBytes = 4 * kTwSlots * sizeof(uint4);
+constexpr size_t kPersistGroupBytes = 4 * kPE * sizeof(uint4);
+
+__device__ __forceinline__ uint32_t swz4(uint32_t i) { return i ^ ((i >> 3) & 1u) ^ (((i >> 4) & 1u) * 6u); }
+__device__ __forceinline__ uint32_t tsw(uint32_t e) { return e ^ ((e >> 3) & 7u) ^ ((e >> 6) & 7u); }
+__device__ __forceinline__ Fr lds4(const uint4* lo, uint32_t i) {
+  const uint32_t p = swz4(i);
+  return fr_pack(lo[p], lo[kPE + p]);
+}
+__device__ __forceinline__ void sts4(uint4* lo, uint32_t i, const Fr& x) {
+  const uint32_t p = swz4(i);
+  lo[p] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+  lo[kPE + p] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+__device__ __forceinline__ void group_sync(uint32_t id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ bool group_any(uint32_t id, bool pred) {
+  uint32_t r;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 256, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r)
+      : "r"((uint32_t)pred), "r"(id)
+      : "memory");
+  return r != 0;
+}
+// Y * omega^e with the twiddle planes at shared address tw (entry e at slot tsw(e))
+__device__ __forceinline__ Fr mul_tw_sm(const Fr& y, uint32_t tw, uint32_t e) {
+  const uint32_t a = tw + (tsw(e) << 4);
+  return fr_mul_shoup_sm(y, a, a + kTwSlots * 16, a + 2 * kTwSlots * 16, a + 3 * kTwSlots * 16);
+}
+__device__ __forceinline__ void bfly_dit_sm(Fr& X, Fr& Y, uint32_t tw, uint32_t e) {
+  lz_csub2r(X);
+  const Fr T = mul_tw_sm(Y, tw, e);
+  Y = lz_add(X, lz_2r_minus(T));
+  X = lz_add(X, T);
+}
+// inverse butterfly with omega^-i read as -omega^(512-i): (X, Y) -> (X + Y, (Y - X) omega^(512-i))
+__device__ __forceinline__ void bfly_dif_sm(Fr& X, Fr& Y, uint32_t tw, uint32_t i) {
+  const Fr D = lz_add(Y, lz_3r_minus(X));
+  X = lz_add(X, Y);
+  lz_csub2r(X);
+  Y = mul_tw_sm(D, tw, 512u - i);
+}
+// the two stages s, s+1 of a size-1024 transform on the four elements of one thread (x[e]: index bits s, s+1 = e)
+template <bool DIF>
+__device__ __forceinline__ void bfly4_sm(Fr (&x)[4], uint32_t t_lo, int s, uint32_t tw) {
+  if (!DIF) {
+    if (s == 0) {
+      lz_bfly_dit1(x[0], x[1]);
+      lz_bfly_dit1(x[2], x[3]);
+      lz_bfly_dit1(x[0], x[2]);
+      bfly_dit_sm(x[1], x[3], tw, 256u);
+    } else {
+      const uint32_t e0 = t_lo << (9 - s);
+      bfly_dit_sm(x[0], x[1], tw, e0);
+      bfly_dit_sm(x[2], x[3], tw, e0);
+      const uint32_t e1 = t_lo << (8 - s);
+      bfly_dit_sm(x[0], x[2], tw, e1);
+      bfly_dit_sm(x[1], x[3], tw, e1 | 256u);
+    }
+  } else {
+    if (s == 0) {
+      lz_bfly_dif1(x[0], x[2]);
+      bfly_dif_sm(x[1], x[3], tw, 256u);
+      lz_bfly_dif1(x[0], x[1]);
+      lz_bfly_dif1(x[2], x[3]);
+    } else {
+      const uint32_t e1 = t_lo << (8 - s);
+      bfly_dif_sm(x[0], x[2], tw, e1);
+      bfly_dif_sm(x[1], x[3], tw, e1 | 256u);
+      const uint32_t e0 = t_lo << (9 - s);
+      bfly_dif_sm(x[0], x[1], tw, e0);
+      bfly_dif_sm(x[2], x[3], tw, e0);
+    }
+  }
+}
+template <bool DIF>
+__device__ __forceinline__ void pass4_inplace(uint4* buf, int s, uint32_t t, uint32_t tw) {
+  const uint32_t t_lo = t & ((1u << s) - 1u), base = ((t >> s) << (s + 2)) | t_lo;
+  Fr x[4];
+#pragma unroll
+  for (int e = 0; e < 4; e++) x[e] = lds4(buf, base | ((uint32_t)e << s));
+  bfly4_sm<DIF>(x, t_lo, s, tw);
+#pragma unroll
+  for (int e = 0; e < 4; e++) sts4(buf, base | ((uint32_t)e << s), x[e]);
+}
+
+template <int GROUPS>
+__global__ void __launch_bounds__(GROUPS* kPT, 1) ntt_persist_kernel(const __grid_constant__ LocalArgs a) {
+  extern __shared__ uint4 smem[];
+  // one copy of the order-1024 twiddles per SM
+  for (uint32_t e = threadIdx.x; e <= 512; e += GROUPS * kPT) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.w_fwd + e);
+    const uint32_t p = tsw(e);
+#pragma unroll
+    for (int pl = 0; pl < 4; pl++) smem[pl * kTwSlots + p] = __ldg(src + pl);
+  }
+  __syncthreads();
+  const uint32_t t = threadIdx.x & (kPT - 1), gi = threadIdx.x / kPT, bar = 1 + gi;
+  const uint32_t tw = (uint32_t)__cvta_generic_to_shared(smem);
+  uint4* A = smem + 4 * kTwSlots + (size_t)gi * 4 * kPE;
+  uint4* B = A + 2 * kPE;
+  const unsigned long long nchunks = a.total >> kLogPE;
+  const uint32_t col_mask = (1u << a.q) - 1u;
+  const bool copy0 = a.mapped ? a.copy0 != 0 : a.plane0 != nullptr;
+  for (unsigned long long ch = (unsigned long long)blockIdx.x * GROUPS + gi; ch < nchunks;
+       ch += (unsigned long long)gridDim.x * GROUPS) {
+    const unsigned long long f0 = ch << kLogPE;
+    Fr x[4];
+    uint32_t nz = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      x[e] = ld_fr(a.in + f0 + t + kPT * e);
+      nz |= fr_or(x[e]);
+    }
+    if (copy0) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const Fr x0 = a.plain0 ? fr_from_mont(x[e]) : x[e];
+        if (a.mapped) st_mapped(a, 0, f0 + t + kPT * e, x0);
+        else st_fr(a.plane0 + f0 + t + kPT * e, x0);
+      }
+    }
+    // (the barrier also orders the previous chunk's last reads of B before this chunk's first writes)
+    if (!group_any(bar, nz != 0)) {  // all-zero chunk: the codeword is zero
+      const Fr z = fr_zero();
+      for (int cs = 1; cs < a.rho; cs++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const unsigned long long f = f0 + t + kPT * e;
+          if (a.mapped) st_mapped(a, cs, f, z);
+          else st_fr(a.out + (cs - 1) * a.plane_stride + f, z);
+        }
+      continue;
+    }
+    // inverse tail: DIF stages 9..0; the first pass works on the registers just loaded (thread t holds t + 256 e)
+    bfly4_sm<true>(x, t, 8, tw);
+#pragma unroll
+    for (int e = 0; e < 4; e++) sts4(A, t | ((uint32_t)e << 8), x[e]);
+    group_sync(bar);
+#pragma unroll 1
+    for (int s = 6; s >= 0; s -= 2) {
+      pass4_inplace<true>(A, s, t, tw);
+      group_sync(bar);
+    }
+    // cosets 1 .. rho-1: scale while loading A, DIT stages 0..9 in B, the last pass stores to global memory
+    const uint4* sc = a.scale4 + (size_t)((uint32_t)(f0 & col_mask) >> kLogPE) * (4 * kPE) + t;
+    const size_t sc_stride = ((size_t)1 << (a.q - kLogPE)) * (4 * kPE);
+#pragma unroll 1
+    for (int cs = 1; cs < a.rho; cs++, sc += sc_stride) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) x[e] = fr_mul_shoup_g4(lds4(A, (t << 2) | (uint32_t)e), sc + e * kPT, kPE);
+      bfly4_sm<false>(x, 0, 0, tw);
+#pragma unroll
+      for (int e = 0; e < 4; e++) sts4(B, (t << 2) | (uint32_t)e, x[e]);
+      group_sync(bar);
+#pragma unroll 1
+      for (int s = 2; s <= 6; s += 2) {
+        pass4_inplace<false>(B, s, t, tw);
+        group_sync(bar);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) x[e] = lds4(B, t | ((uint32_t)e << 8));
+      bfly4_sm<false>(x, t, 8, tw);
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const unsigned long long f = f0 + t + kPT * e;
+        const Fr v = a.final ? fr_normalize(x[e]) : x[e];
+        if (a.mapped) st_mapped(a, cs, f, v);
+        else st_fr(a.out + (cs - 1) * a.plane_stride + f, v);
+      }
+      group_sync(bar);  // B is rewritten by the next coset's first pass
+    }
+  }
+}
+
+// SoA copy of the coset scale tables for ntt_persist_kernel (NttTables::scale4)
+__global__ void scale_soa_kernel(const FrTw* __restrict__ scale, uint4* __restrict__ out, size_t count) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // entry index: (coset-1)*k + position
+  if (i >= count) return;
+  const size_t chunk = i >> kLogPE;
+  const uint32_t idx = (uint32_t)i & (kPE - 1), slot = (idx & 3u) * kPT + (idx >> 2);
+  const uint4* src = reinterpret_cast<const uint4*>(scale + i);
+#pragma unroll
+  for (int pl = 0; pl < 4; pl++) out[chunk * (4 * kPE) + (size_t)pl * kPE + slot] = src[pl];
+}
+
 // table generation: p = floor(w 2^256 / r) for every entry
 __global__ void fill_quotients_kernel(FrTw* t, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -365,9 +575,11 @@ int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool pla
   const size_t k = (size_t)1 << log_k, half = k / 2 ? k / 2 : 1;
   // Montgomery-form powers on the host, then every entry becomes {plain integer, 0}; the quotient
   // multipliers are filled in on the device (fill_quotients_kernel)
-  std::vector<FrTw> tab(2 * half + (size_t)(rho_inv - 1) * k);
+  // w_fwd carries one extra entry, omega^(k/2) = -1: the persistent encoder reads its inverse twiddles as
+  // omega^-i = -omega^(k/2 - i) from the forward table, i = 0 included
+  std::vector<FrTw> tab(2 * half + 1 + (size_t)(rho_inv - 1) * k);
   FrTw* wf = tab.data();
-  FrTw* wi = wf + half;
+  FrTw* wi = wf + half + 1;
   FrTw* sc = wi + half;
   const Fr w = fr_root_of_unity(log_k), winv = fr_inv(w);
   Fr a = fr_one(), b = fr_one();
@@ -378,6 +590,8 @@ int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool pla
     a = fr_mul(a, w);
     b = fr_mul(b, winv);
   }
+  wf[half].w = fr_from_mont(a);  // omega^(k/2) (= r - 1 for k >= 2)
+  wf[half].p = fr_zero();
   const Fr g = fr_root_of_unity(log_k + log_rho);
   const Fr kinv = fr_inv(fr_from_u64(k));
   std::vector<Fr> pw(k);
@@ -406,8 +620,16 @@ int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool pla
   LG_CUDA(ctx, cudaGetLastError());
   LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the host vector dies at scope exit
   t.w_fwd = dev;
-  t.w_inv = dev + half;
-  t.scale = dev + 2 * half;
+  t.w_inv = dev + half + 1;
+  t.scale = dev + 2 * half + 1;
+  if (log_k >= kLogPE && rho_inv > 1) {
+    const size_t cnt = (size_t)(rho_inv - 1) * k;
+    LG_CUDA(ctx, cudaMalloc(&t.scale4, cnt * sizeof(FrTw)));
+    scale_soa_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(t.scale, t.scale4, cnt);
+    ctx->launches++;
+    LG_CUDA(ctx, cudaGetLastError());
+    LG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   auto ins = ctx->tables.emplace(key, t);
   *out = &ins.first->second;
   return OK;
@@ -489,6 +711,40 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
   return launch_local_v<kMaxR, kMinB, MODE>(ctx, a);
 }
 
+// persistent encoder: one CTA per SM; LG_NTT_PERSIST=0 falls back to ntt_local_kernel, LG_NTT_GROUPS=2 runs two
+// groups per SM (leaves a third of the registers to a co-resident column-hash kernel) -- tuning hooks
+static int persist_groups() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LG_NTT_PERSIST");
+    v = (e && atoi(e) == 0) ? 0 : 3;
+    if (v) {
+      const char* g = getenv("LG_NTT_GROUPS");
+      if (g && atoi(g) == 2) v = 2;
+    }
+  }
+  return v;
+}
+template <int GROUPS>
+static int launch_persist_g(Ctx* ctx, const LocalArgs& a) {
+  const size_t smem = kPersistTwBytes + GROUPS * kPersistGroupBytes;
+  static bool configured = false;
+  if (!configured) {
+    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_persist_kernel<GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const unsigned long long chunks = a.total >> kLogPE;
+  unsigned long long ctas = (chunks + GROUPS - 1) / GROUPS;
+  if (ctas > (unsigned long long)ctx->sm_count) ctas = ctx->sm_count;
+  ntt_persist_kernel<GROUPS><<<(unsigned)ctas, GROUPS * kPT, smem, ctx->stream>>>(a);
+  ctx->launches++;
+  LG_CUDA(ctx, cudaGetLastError());
+  return OK;
+}
+static int launch_persist(Ctx* ctx, const LocalArgs& a, int groups) {
+  return groups == 2 ? launch_persist_g<2>(ctx, a) : launch_persist_g<3>(ctx, a);
+}
+
 template <int R, bool DIF, bool COPY0>
 static int launch_global_pass_mapped(Ctx* ctx, const Fr* in, Fr* out, size_t rows, int q, int s, const FrTw* W,
                                      const OutMap& map, uint32_t rows_per_plane, int copy_plain) {
@@ -559,7 +815,12 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
     a.mapped = map ? 1 : 0;
     a.copy0 = map ? 1 : 0;
   }
-  LG_TRY(launch_local<0>(ctx, a));
+  if (l == kLogPE && rho_inv > 1 && persist_groups()) {
+    a.scale4 = t->scale4;
+    LG_TRY(launch_persist(ctx, a, persist_groups()));
+  } else {
+    LG_TRY(launch_local<0>(ctx, a));
+  }
   phase_mark(ctx, PH_NTT_LOCAL);
   if (q > l && rho_inv > 1) {
     Fr* p = cosets;
