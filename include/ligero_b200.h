@@ -305,6 +305,68 @@ int lg_proof_assemble(const uint8_t root[32], const uint64_t* preenc_u_lc, size_
 int lg_proof_serialize(const lg_proof* p, uint8_t* buf, size_t cap, size_t* len_out);
 int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out);
 
+/* =====================================================================================================
+ * Multi-GPU prover behind the boundary (capi_shard.cu).  The reference's prover is one call,
+ * LigeroCircuit::prove (src/ligero/mod.rs:435-455); these entry points let that one call reach G GPUs.
+ *
+ * lg_shard = one GPU's part: it encodes a share of the rows of [X;Y;Z;W] and owns the columns
+ * [rank*n/G, (rank+1)*n/G) of the committed matrix (hash, Merkle subtree, the three tests and the openings of
+ * those columns).  Ranks exchange data only through peer-mapped device memory over NVLink (codeword elements from
+ * inside the encode kernels; roots, test evaluations and authentication paths through per-rank mailboxes with
+ * device-side flags), so the same code runs as one process per GPU (CUDA IPC handles carried by the host's
+ * launcher: lg_shard_handles / lg_shard_connect) and as one process driving every GPU (lg_mgpu_*).
+ * Every rank of a group must make the same sequence of lg_shard_commit* / lg_shard_prove* calls.
+ * ===================================================================================================== */
+typedef struct lg_shard lg_shard;
+/* m, k, rho_inv: shape of the commitment (4m rows); t_max: openings per test (0: commitment only, no prover
+ * buffers); sub_blocks >= 1: each of the X, Y, Z, W blocks is encoded in that many pipeline steps (see
+ * lg_shard_layout).  world a power of two <= 8, k divisible by world. */
+int lg_shard_create(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_inv, int rank, int world, size_t t_max, int sub_blocks,
+                    lg_shard** out);
+int lg_shard_free(lg_shard* s);
+/* three CUDA IPC handles (codeword shard, r-hat shard, mailbox), 64 bytes each */
+int lg_shard_handles(lg_shard* s, uint8_t out[192]);
+/* all_handles: world x 192 bytes in rank order (this rank's own entry is ignored) */
+int lg_shard_connect(lg_shard* s, const uint8_t* all_handles);
+/* the same for shards that live in ONE process (enables peer access between their devices) */
+int lg_shard_connect_local(lg_shard* const* shards, int world);
+/* hash the row blocks that have arrived behind the encoding of the next (default on; LG_SHARD_PIPELINE=0) */
+int lg_shard_set_pipeline(lg_shard* s, int enabled);
+/* This rank's rows: 4*sub_blocks runs of consecutive global rows, in the order its local matrix stores them
+ * (with sub_blocks = 1: [X_g; Y_g; Z_g; W_g]).  row_base / nrows: capacity 4*sub_blocks each, nullable. */
+int lg_shard_layout(const lg_shard* s, size_t* rows_local, size_t* n_runs, size_t* row_base, size_t* nrows);
+/* the rank's column shard as a matrix handle (rows x k/world columns; read-backs, tests) */
+lg_matrix* lg_shard_matrix(lg_shard* s);
+/* encode + commit (src/ligero/mod.rs:521-551) of this rank's rows, Fr[rows_local * k], host or device.
+ * _async enqueues everything and returns; lg_shard_root synchronises and folds the G subtree roots into the root. */
+int lg_shard_commit_async(lg_shard* s, const uint64_t* msg_local);
+int lg_shard_root(lg_shard* s, uint8_t root_out[32], uint8_t* subtree_roots_out /* world*32, nullable */);
+int lg_shard_commit(lg_shard* s, const uint64_t* msg_local, uint8_t root_out[32]);
+/* prove_inner (457-578) on this rank's rows of a ready pre-encoding matrix / prove (435-455) from the variable
+ * assignment (the evaluation trace runs replicated on every GPU).  Every rank advances its own copy of the sponge
+ * through the same transcript and gets the same proof; out may be NULL for ranks whose proof nobody reads. */
+int lg_shard_prove_matrix(lg_shard* s, lg_ligero* l, const uint64_t* local_rows, lg_sponge* sponge, lg_proof** out);
+int lg_shard_prove(lg_shard* s, lg_ligero* l, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump,
+                   lg_sponge* sponge, lg_proof** out);
+/* host wall clock of the last lg_shard_prove_matrix, ms: [0] commit, [1] whole call */
+int lg_shard_last_ms(const lg_shard* s, double ms_out[4]);
+
+/* One process, G GPUs: what a Rust `LigeroCircuit::prove` binds to reach the whole box in one call. */
+typedef struct lg_mgpu lg_mgpu;
+typedef struct lg_mligero lg_mligero;
+int lg_mgpu_create(const int* dev_ids /* NULL: 0..n_dev-1 */, int n_dev, lg_mgpu** out);
+int lg_mgpu_destroy(lg_mgpu* g);
+const char* lg_mgpu_last_error(const lg_mgpu* g);
+lg_ctx* lg_mgpu_ctx(lg_mgpu* g, int i);
+/* encode + commit of a whole rows x k host matrix over all GPUs (root only) */
+int lg_mgpu_commit(lg_mgpu* g, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, uint8_t root_out[32]);
+/* LigeroCircuit::new on every GPU + the shards of its commitment */
+int lg_mgpu_ligero_new(lg_mgpu* g, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_mligero** out);
+int lg_mgpu_ligero_free(lg_mligero* ml);
+/* LigeroCircuit::prove / prove_inner over all GPUs: same proof bytes as lg_prove, same sponge advance */
+int lg_mgpu_prove(lg_mligero* ml, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge,
+                  lg_proof** out);
+
 /* ---- measured integer roofline ----------------------------------------------------------------- */
 /* Runs dependent-chain microbenchmarks at full occupancy for ~`ms_target` milliseconds each and
  * reports sustained Montgomery multiplications/s and IMAD.WIDE.U32 (32x32+64) operations/s. */

@@ -117,6 +117,28 @@ SIGNATURES = {
     "lg_proof_free": (c_int, [c_void_p]),
     "lg_proof_serialize": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t)]),
     "lg_proof_deserialize": (c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    "lg_shard_create": (c_int, [c_void_p, c_size_t, c_size_t, c_uint32, c_int, c_int, c_size_t, c_int, POINTER(c_void_p)]),
+    "lg_shard_free": (c_int, [c_void_p]),
+    "lg_shard_handles": (c_int, [c_void_p, c_void_p]),
+    "lg_shard_connect": (c_int, [c_void_p, c_void_p]),
+    "lg_shard_connect_local": (c_int, [POINTER(c_void_p), c_int]),
+    "lg_shard_set_pipeline": (c_int, [c_void_p, c_int]),
+    "lg_shard_layout": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), c_void_p, c_void_p]),
+    "lg_shard_matrix": (c_void_p, [c_void_p]),
+    "lg_shard_commit_async": (c_int, [c_void_p, c_void_p]),
+    "lg_shard_root": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lg_shard_commit": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "lg_shard_prove_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
+    "lg_shard_prove": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, POINTER(c_void_p)]),
+    "lg_shard_last_ms": (c_int, [c_void_p, POINTER(c_double)]),
+    "lg_mgpu_create": (c_int, [c_void_p, c_int, POINTER(c_void_p)]),
+    "lg_mgpu_destroy": (c_int, [c_void_p]),
+    "lg_mgpu_last_error": (c_char_p, [c_void_p]),
+    "lg_mgpu_ctx": (c_void_p, [c_void_p, c_int]),
+    "lg_mgpu_commit": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint32, c_void_p]),
+    "lg_mgpu_ligero_new": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, POINTER(c_void_p)]),
+    "lg_mgpu_ligero_free": (c_int, [c_void_p]),
+    "lg_mgpu_prove": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p, POINTER(c_void_p)]),
     "lg_intt": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t]),
     "lg_bench_int_peak": (c_int, [c_void_p, c_double, POINTER(c_double), POINTER(c_double)]),
     "lg_bench_shoup_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),

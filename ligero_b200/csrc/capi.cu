@@ -215,7 +215,7 @@ static int stage_input(lg_ctx* ctx, const uint64_t* src, size_t elems, const Fr*
 }
 
 // second stream (lowest priority: it only fills what the encoder leaves free) + per-column state for tile-wise hashing
-static int hash_pipeline_setup(Ctx* c, size_t n) {
+int hash_pipeline_setup(Ctx* c, size_t n) {
   if (!c->hash_stream) {
     int lo = 0, hi = 0;
     LG_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -450,7 +450,9 @@ int lg_ctx_create(int device, lg_ctx** out) {
   // then only fills the registers and issue slots the encoder leaves free
   int prio_lo = 0, prio_hi = 0;
   cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-  if (cudaStreamCreateWithPriority(&ctx->c.stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+  // (one step below the greatest priority, which is kept for the latency-bound hash stream of the multi-GPU pipeline)
+  const int prio_main = prio_hi < prio_lo ? prio_hi + 1 : prio_hi;
+  if (cudaStreamCreateWithPriority(&ctx->c.stream, cudaStreamNonBlocking, prio_main) != cudaSuccess) {
     delete ctx;
     return ERR_CUDA;
   }
@@ -466,6 +468,9 @@ int lg_ctx_create(int device, lg_ctx** out) {
     cudaGetLastError();
   }
   if (const char* e = getenv("LG_OVERLAP")) ctx->c.overlap = atoi(e) != 0;  // tuning hook; see lg_ctx_set_overlap
+  if (const char* e = getenv("LG_NTT_PERSIST")) ctx->c.persist_groups = atoi(e) == 0 ? 0 : 3;
+  if (const char* e = getenv("LG_NTT_GROUPS"))
+    if (ctx->c.persist_groups && atoi(e) == 2) ctx->c.persist_groups = 2;
   if (const char* e = getenv("LG_HASH_QUAD_MAX")) ctx->c.hash_quad_max = (size_t)strtoull(e, nullptr, 10);
   *out = ctx;
   return OK;
@@ -488,6 +493,10 @@ int lg_ctx_destroy(lg_ctx* ctx) {
       if (ctx->c.ev_consumed[i]) cudaEventDestroy(ctx->c.ev_consumed[i]);
     }
     cudaStreamDestroy(ctx->c.copy_stream);
+  }
+  if (ctx->c.hash_stream_hi) {
+    cudaStreamSynchronize(ctx->c.hash_stream_hi);
+    cudaStreamDestroy(ctx->c.hash_stream_hi);
   }
   if (ctx->c.hash_stream) {
     cudaStreamSynchronize(ctx->c.hash_stream);

@@ -74,6 +74,14 @@ struct Ctx {
   // commit pipeline: column hashing of row tile i (high-priority stream) overlaps the encoding of tile i+1
   double last_shoup_peak[2] = {0, 0};  // lg_bench_int_peak: table-constant products/s, lazy butterflies/s
   bool overlap = true;
+  // groups of 256 threads per SM in the persistent encoder (ntt.cu): 3 = every register of the SM, 2 = capped at 88
+  // registers so that four CTAs of a co-resident column-hash kernel fit beside it (multi-GPU block pipeline);
+  // 0 = the one-CTA-per-chunk kernel.  LG_NTT_PERSIST=0 / LG_NTT_GROUPS=2 in the environment set the default.
+  int persist_groups = 3;
+  // multi-GPU block pipeline (capi_shard.cu): the column hash of the row blocks that have landed runs on this stream,
+  // one priority step ABOVE the context stream -- a column's BLAKE2s chain is latency bound, so its few warps must be
+  // resident and scheduled first; the encoder fills the rest of the SM
+  cudaStream_t hash_stream_hi = nullptr;
   cudaStream_t hash_stream = nullptr;
   cudaEvent_t ev_encoded = nullptr, ev_hashed = nullptr;
   uint32_t* hash_state = nullptr;
@@ -96,6 +104,8 @@ enum Phase : int { PH_BEGIN = -1, PH_NTT_STRIDED_INV = 0, PH_NTT_LOCAL = 1, PH_N
 void phase_mark(Ctx* ctx, int phase_ended);
 
 int ctx_scratch(Ctx* ctx, size_t bytes, void** out);
+// second stream + events + per-column BLAKE2s state for tile-wise column hashing of an n-column matrix (capi.cu)
+int hash_pipeline_setup(Ctx* c, size_t n);
 int ctx_host_stage(Ctx* ctx, size_t bytes, void** out);  // pinned, reused across calls (one host thread per context)
 // plain: the coset scale factors carry an extra R^-1, so the coset planes come out as plain integers
 int get_tables(Ctx* ctx, int log_k, int rho_inv, const NttTables** out, bool plain = false);

@@ -443,8 +443,11 @@ __device__ __forceinline__ void pass4_inplace(uint4* buf, int s, uint32_t t, uin
   for (int e = 0; e < 4; e++) sts4(buf, base | ((uint32_t)e << s), x[e]);
 }
 
-template <int GROUPS>
-__global__ void __launch_bounds__(GROUPS* kPT, 1) ntt_persist_kernel(const __grid_constant__ LocalArgs a) {
+// CAPPED: at most 88 registers per thread (two groups: 45 K of the SM's 64 K registers, the rest is left to a co-resident
+// column-hash kernel -- the multi-GPU block pipeline of capi_shard.cu)
+template <int GROUPS, bool CAPPED>
+__global__ void __launch_bounds__(GROUPS* kPT, 1) __maxnreg__(CAPPED ? 88 : 255)
+    ntt_persist_kernel(const __grid_constant__ LocalArgs a) {
   extern __shared__ uint4 smem[];
   // one copy of the order-1024 twiddles per SM
   for (uint32_t e = threadIdx.x; e <= 512; e += GROUPS * kPT) {
@@ -711,38 +714,25 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
   return launch_local_v<kMaxR, kMinB, MODE>(ctx, a);
 }
 
-// persistent encoder: one CTA per SM; LG_NTT_PERSIST=0 falls back to ntt_local_kernel, LG_NTT_GROUPS=2 runs two
-// groups per SM (leaves a third of the registers to a co-resident column-hash kernel) -- tuning hooks
-static int persist_groups() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("LG_NTT_PERSIST");
-    v = (e && atoi(e) == 0) ? 0 : 3;
-    if (v) {
-      const char* g = getenv("LG_NTT_GROUPS");
-      if (g && atoi(g) == 2) v = 2;
-    }
-  }
-  return v;
-}
-template <int GROUPS>
+// persistent encoder: one CTA per SM; Ctx::persist_groups picks the variant
+template <int GROUPS, bool CAPPED>
 static int launch_persist_g(Ctx* ctx, const LocalArgs& a) {
   const size_t smem = kPersistTwBytes + GROUPS * kPersistGroupBytes;
   static bool configured = false;
   if (!configured) {
-    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_persist_kernel<GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_persist_kernel<GROUPS, CAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   const unsigned long long chunks = a.total >> kLogPE;
   unsigned long long ctas = (chunks + GROUPS - 1) / GROUPS;
   if (ctas > (unsigned long long)ctx->sm_count) ctas = ctx->sm_count;
-  ntt_persist_kernel<GROUPS><<<(unsigned)ctas, GROUPS * kPT, smem, ctx->stream>>>(a);
+  ntt_persist_kernel<GROUPS, CAPPED><<<(unsigned)ctas, GROUPS * kPT, smem, ctx->stream>>>(a);
   ctx->launches++;
   LG_CUDA(ctx, cudaGetLastError());
   return OK;
 }
 static int launch_persist(Ctx* ctx, const LocalArgs& a, int groups) {
-  return groups == 2 ? launch_persist_g<2>(ctx, a) : launch_persist_g<3>(ctx, a);
+  return groups == 2 ? launch_persist_g<2, true>(ctx, a) : launch_persist_g<3, false>(ctx, a);
 }
 
 template <int R, bool DIF, bool COPY0>
@@ -815,9 +805,9 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
     a.mapped = map ? 1 : 0;
     a.copy0 = map ? 1 : 0;
   }
-  if (l == kLogPE && rho_inv > 1 && persist_groups()) {
+  if (l == kLogPE && rho_inv > 1 && ctx->persist_groups) {
     a.scale4 = t->scale4;
-    LG_TRY(launch_persist(ctx, a, persist_groups()));
+    LG_TRY(launch_persist(ctx, a, ctx->persist_groups));
   } else {
     LG_TRY(launch_local<0>(ctx, a));
   }

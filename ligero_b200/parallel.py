@@ -1,4 +1,7 @@
-"""Multi-GPU encode + commit: one process per GPU, torch.distributed (NCCL over NVLink) for plumbing.
+"""Multi-GPU encode + commit + prove, one process per GPU: a veneer over the C ABI's lg_shard_* (capi_shard.cu).
+torch.distributed (NCCL) is used for rendezvous only -- exchanging the CUDA IPC handles once, aligning the ranks and
+reducing the timing; the data path (codeword scatter, subtree roots, test evaluations, authentication paths) runs
+inside the library over NVLink peer memory with device-side flags.
 
 Sharding (north_star):
   1. rows: rank g owns the rows {b*m + i : b in X,Y,Z,W ; i in its slice of [0, m)} -- a 4*m_g-row
@@ -40,10 +43,16 @@ def block_slices(m: int, world: int) -> List[Tuple[int, int]]:
     return out
 
 
-def local_row_ids(m: int, world: int, rank: int) -> List[int]:
-    """global row indices (into the 4m-row matrix) owned by `rank`, in local order [X_g; Y_g; Z_g; W_g]."""
-    i0, i1 = block_slices(m, world)[rank]
-    return [b * m + i for b in range(4) for i in range(i0, i1)]
+def local_row_ids(m: int, world: int, rank: int, sub_blocks: int = 1) -> List[int]:
+    """global row indices (into the 4m-row matrix) owned by `rank`, in local order: for every block b in X, Y, Z, W and
+    every sub-block u (m rows split into `sub_blocks` runs like block_slices) the rank's slice of that sub-block.
+    With sub_blocks = 1 this is [X_g; Y_g; Z_g; W_g].  Mirrors lg_shard_layout."""
+    out = []
+    for b in range(4):
+        for (s0, s1) in block_slices(m, sub_blocks):
+            a, e = block_slices(s1 - s0, world)[rank]
+            out.extend(b * m + s0 + i for i in range(a, e))
+    return out
 
 
 def pack_for_exchange(u_rows: torch.Tensor, rho: int, rows_g: int, k: int, world: int) -> List[torch.Tensor]:
@@ -127,161 +136,75 @@ def exchange(send: List[torch.Tensor], recv: List[torch.Tensor]) -> None:
 
 
 # --------------------------------------------------------------------------------------------
-# device path
+# device path: veneer over lg_shard_* (one lg_shard per rank)
 # --------------------------------------------------------------------------------------------
-def open_peer_shards(ctx, rows: int, kg: int, rho: int, rank: int, world: int):
-    """One column-shard matrix (rows x kg, rho planes) per rank, each mapped into every peer with CUDA IPC.
-    Returns (this rank's CommittedMatrix, ctypes array of the `world` shard base pointers, peer pointers to close)."""
+def _make_shard(ctx, m: int, k: int, rho: int, rank: int, world: int, t_max: int, sub_blocks: int):
+    """lg_shard_create + IPC handle exchange (the only use of torch.distributed besides barriers) + lg_shard_connect"""
     from ctypes import byref, c_void_p
     import numpy as np
-    from .backend import CommittedMatrix, check
+    from .backend import check
     h = c_void_p()
-    check(ctx.lib.lg_matrix_create(ctx.handle, rows, kg, rho, byref(h)), ctx.handle, "lg_matrix_create")
-    mat = CommittedMatrix(ctx, h, None)
-    handle = np.zeros(64, dtype=np.uint8)
-    check(ctx.lib.lg_ipc_export(mat.handle, handle.ctypes.data), ctx.handle, "lg_ipc_export")
-    handles = [None] * world
-    dist.all_gather_object(handles, bytes(handle))
-    ptrs, peers = [], []
-    for g in range(world):
-        if g == rank:
-            ptrs.append(int(ctx.lib.lg_matrix_u_dev(mat.handle)))
-        else:
-            p = c_void_p()
-            hb = np.frombuffer(handles[g], dtype=np.uint8).copy()
-            check(ctx.lib.lg_ipc_open(ctx.handle, hb.ctypes.data, byref(p)), ctx.handle, "lg_ipc_open")
-            ptrs.append(int(p.value))
-            peers.append(int(p.value))
-    return mat, (c_void_p * world)(*ptrs), peers
+    check(ctx.lib.lg_shard_create(ctx.handle, m, k, rho, rank, world, t_max, sub_blocks, byref(h)), ctx.handle, "lg_shard_create")
+    mine = np.zeros(192, dtype=np.uint8)
+    check(ctx.lib.lg_shard_handles(h, mine.ctypes.data), ctx.handle, "lg_shard_handles")
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine))
+        blob = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+    else:
+        blob = mine
+    check(ctx.lib.lg_shard_connect(h, blob.ctypes.data), ctx.handle, "lg_shard_connect")
+    if world > 1:
+        dist.barrier()
+    return h
 
 
 class ShardedCommitter:
-    """Row-sharded encode -> exchange -> column-sharded hash + subtree -> root all-gather.
+    """Row-sharded encode -> NVLink scatter fused into the encode kernels -> column-sharded hash + subtree -> root.
+    `pipeline` (default on): the X, Y, Z, W row blocks (times `sub_blocks`) are encoded one after the other and the
+    column owner hashes each block, on a higher-priority stream, while the next one is encoded and delivered."""
 
-    mode "fused" (default): the exchange is fused into the encode kernels -- the last NTT pass stores each
-        finished element directly into the owning rank's column shard over NVLink peer memory (CUDA IPC
-        mappings exchanged once at construction), so the transfer overlaps the butterflies and there is no
-        pack / all-to-all / unpack.  The four row blocks X, Y, Z, W are encoded one after the other; after
-        each, one tiny NCCL all-reduce tells every rank that the block has landed everywhere and the column
-        owner hashes those rows on its second stream WHILE the next block is encoded and delivered: a column
-        hash is a sequential chain per column (`pipeline=False` hashes after the last block instead; the
-        default picks by world size from measurements, see __init__).
-    mode "nccl": encode locally, then pack -> NCCL all_to_all -> unpack (the plain-library baseline, and the
-        plumbing the gloo tests cover).
-    """
-
-    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int, mode: str = "fused", pipeline=None):
+    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int, pipeline=None, sub_blocks: int = 1, t_max: int = 0):
         assert world & (world - 1) == 0 and k % world == 0 and (rho * k // world) >= 2
-        assert mode in ("fused", "nccl")
-        self.ctx, self.m, self.k, self.rho, self.rank, self.world, self.mode = ctx, m, k, rho, rank, world, mode
-        if pipeline is None:
-            # measured on 8 x B200 (2^24-gate shape): the block pipeline wins at 2 GPUs (78.6 vs 81.9 ms) and loses
-            # at 4 and 8 (44.3 vs 41.7, 31.6 vs 26.2 ms), where the hash is a pure latency chain that the encoder's
-            # warps on the same SM slow down more than the overlap gains
-            pipeline = world <= 2
-        self.pipeline = bool(pipeline) and mode == "fused"
-        self.slices = block_slices(m, world)
-        i0, i1 = self.slices[rank]
-        self.i0, self.m_g = i0, i1 - i0
-        self.rows_g = 4 * self.m_g
-        self.kg = k // world
-        dev = torch.device("cuda", ctx.device)
-        self.dev = dev
-        self.stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-        self.roots = torch.empty((world, 32), dtype=torch.uint8, device=dev)
-        self.my_root = torch.empty(32, dtype=torch.uint8, device=dev)
-        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._peer_ptrs = []
-        if mode == "nccl":
-            self.u_rows = torch.empty((rho, max(self.rows_g, 1), k, 4), dtype=torch.int64, device=dev)
-            self.u_cols = torch.empty((rho, 4 * m, self.kg, 4), dtype=torch.int64, device=dev)
-            self.recv = [torch.empty((rho, 4 * (b - a), self.kg, 4), dtype=torch.int64, device=dev) for a, b in self.slices]
-            self.mat_rows = ctx.wrap(self.u_rows, max(self.rows_g, 1), k, rho) if self.rows_g else None
-            self.mat_cols = ctx.wrap(self.u_cols, 4 * m, self.kg, rho)
-        else:
-            self.mat_cols, self.shard_ptrs, self._peer_ptrs = open_peer_shards(ctx, 4 * m, self.kg, rho, rank, world)
-            # local intermediate of the coset planes, only for rows longer than one CTA tile (k > 1024)
-            self.scratch = (torch.empty(((rho - 1) * max(self.rows_g, 1) * k, 4), dtype=torch.int64, device=dev)
-                            if k > 1024 else None)
-            dist.barrier()
+        from .backend import CommittedMatrix, check
+        self.ctx, self.m, self.k, self.rho, self.rank, self.world = ctx, m, k, rho, rank, world
+        self.sub_blocks = sub_blocks
+        self.row_ids = local_row_ids(m, world, rank, sub_blocks)
+        self.rows_g, self.kg = len(self.row_ids), k // world
+        self.handle = _make_shard(ctx, m, k, rho, rank, world, t_max, sub_blocks)
+        if pipeline is not None:
+            check(ctx.lib.lg_shard_set_pipeline(self.handle, int(bool(pipeline))), ctx.handle, "lg_shard_set_pipeline")
+        self.pipeline = pipeline
+        self.dev = torch.device("cuda", ctx.device)
+        self.stream = torch.cuda.ExternalStream(ctx.stream, device=self.dev)
+        self.mat_cols = CommittedMatrix(ctx, ctx.lib.lg_shard_matrix(self.handle), None)
+        self.mat_cols.free = lambda: None            # borrowed: owned by the shard
+        self.subtree_roots = None
 
     def close(self):
-        if self._peer_ptrs:
+        if getattr(self, "handle", None):
             self.ctx.sync()
-            dist.barrier()
-            for p in self._peer_ptrs:
-                self.ctx.lib.lg_ipc_close(self.ctx.handle, p)
-            self._peer_ptrs = []
-            dist.barrier()
-        if getattr(self, "mat_cols", None) is not None:
-            self.mat_cols.free()
+            if self.world > 1:
+                dist.barrier()                           # nobody unmaps a shard a peer may still be writing
+            self.mat_cols.handle = None
+            self.ctx.lib.lg_shard_free(self.handle)
+            self.handle = None
+            if self.world > 1:
+                dist.barrier()
 
-    def commit_async(self, msg_local, marks=None) -> None:
-        """Enqueue everything on the context stream; the root lands in self.roots (device).
-        `marks`: optional list that receives (label, torch.cuda.Event) pairs for per-phase timing."""
+    def commit_async(self, msg_local) -> None:
         from .backend import _ptr, check
-
-        def mark(label):
-            if marks is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record(self.stream)
-                marks.append((label, e))
-        with torch.cuda.stream(self.stream):
-            mark("start")
-            if self.mode == "nccl":
-                if self.mat_rows is not None:
-                    self.mat_rows.encode(msg_local)
-                mark("encode")
-                send = pack_for_exchange(self.u_rows[:, : self.rows_g], self.rho, self.rows_g, self.k, self.world)
-                mark("pack")
-                exchange(send, self.recv)
-                mark("exchange")
-                unpack_after_exchange(self.recv, self.u_cols, self.m, self.world, self.rho, self.kg)
-                mark("unpack")
-            elif self.pipeline:
-                lib, scratch = self.ctx.lib, (_ptr(self.scratch) if self.scratch is not None else None)
-                base = int(_ptr(msg_local).value or 0)
-                for b in range(4):                 # local rows are [X_g; Y_g; Z_g; W_g], 32 bytes per element
-                    off = b * self.m_g * self.k * 32
-                    check(lib.lg_encode_sharded_rows(self.ctx.handle, base + off if self.m_g else None, self.m_g,
-                                                     b * self.m + self.i0, 4 * self.m, self.k, self.rho,
-                                                     self.shard_ptrs, self.world, scratch, 1),
-                          self.ctx.handle, "lg_encode_sharded_rows")
-                    dist.all_reduce(self.flag)      # block b has landed on every rank ...
-                    check(lib.lg_matrix_hash_rows(self.mat_cols.handle, b * self.m, (b + 1) * self.m),
-                          self.ctx.handle, "lg_matrix_hash_rows")   # ... and is hashed behind the next block
-                mark("encode+scatter over NVLink (column hashing of earlier blocks overlapped)")
-                check(lib.lg_matrix_hash_finish(self.mat_cols.handle, None), self.ctx.handle, "lg_matrix_hash_finish")
-                mark("hash tail+subtree")
-            else:
-                check(self.ctx.lib.lg_encode_sharded(self.ctx.handle, _ptr(msg_local), self.m_g, self.k, self.rho,
-                                                     self.shard_ptrs, self.world, self.m, self.i0,
-                                                     _ptr(self.scratch) if self.scratch is not None else None, 1),
-                      self.ctx.handle, "lg_encode_sharded")
-                mark("encode+scatter over NVLink")
-                dist.all_reduce(self.flag)      # every rank's stores have landed before anyone hashes
-                mark("rank barrier")
-            if not self.pipeline:
-                self.mat_cols.hash_async()
-                mark("hash+subtree")
-            # subtree root = node 0 of the local tree (device -> device, stays on the stream)
-            self._copy_root()
-            dist.all_gather_into_tensor(self.roots.view(-1), self.my_root)
-            mark("root all-gather")
-
-    def _copy_root(self):
-        # subtree root = node 0 of the library-owned node array: a stream-ordered D2D copy through torch
-        if getattr(self, "_root_view", None) is None:
-            ptr = int(self.ctx.lib.lg_matrix_nodes_dev(self.mat_cols.handle) or 0)
-            self._root_view = torch.as_tensor(_DevBytes(ptr, 32, self.ctx.device), device=self.my_root.device)
-        self.my_root.copy_(self._root_view)
+        check(self.ctx.lib.lg_shard_commit_async(self.handle, _ptr(msg_local) if self.rows_g else None), self.ctx.handle,
+              "lg_shard_commit_async")
 
     def root(self) -> bytes:
-        """Synchronise and fold the gathered subtree roots into the tree root (host, log2(G) hashes)."""
-        self.ctx.sync()
-        torch.cuda.current_stream().synchronize()
-        r = self.roots.cpu().numpy()
-        return combine_subtree_roots([bytes(r[g]) for g in range(self.world)])
+        import numpy as np
+        from .backend import _ptr, check
+        root = np.zeros(32, dtype=np.uint8)
+        sub = np.zeros((self.world, 32), dtype=np.uint8)
+        check(self.ctx.lib.lg_shard_root(self.handle, _ptr(root), _ptr(sub)), self.ctx.handle, "lg_shard_root")
+        self.subtree_roots = [bytes(sub[g]) for g in range(self.world)]
+        return bytes(root)
 
     def commit(self, msg_local) -> bytes:
         self.commit_async(msg_local)
@@ -289,20 +212,21 @@ class ShardedCommitter:
 
     # ---------------------------------------------------------------------------------------
     @staticmethod
-    def bench(ctx, R: int, k: int, rho: int, args, rank: int, world: int) -> dict:
-        """bench.py's N > 1 path: strong scaling of one R x k encode+commit over `world` GPUs."""
-        mode = os.environ.get("LG_MGPU_MODE", "fused")
+    def bench(ctx, R: int, k: int, rho: int, args, rank: int, world: int, seed: int = 20240, expected_root=None) -> dict:
+        """bench.py's N > 1 path: strong scaling of one R x k encode+commit over `world` GPUs.  Every rank generates its
+        own rows of the SAME seeded matrix (ligero_b200.synthetic), so the root is the one N = 1 and the CPU oracle get."""
+        from .synthetic import matrix_rows_torch
         pipeline = {"0": False, "1": True}.get(os.environ.get("LG_MGPU_PIPELINE", ""), None)
+        sub = int(os.environ.get("LG_MGPU_SUB", "1"))
         m = R // 4
-        sc = ShardedCommitter(ctx, m, k, rho, rank, world, mode, pipeline)
-        dev = torch.device("cuda", ctx.device)
-        g = torch.Generator(device=dev)
-        g.manual_seed(20240 + rank)
-        msg = torch.randint(0, 2 ** 62, (max(sc.rows_g, 1) * k, 4), dtype=torch.int64, device=dev, generator=g)
-        msg[:, 3] &= (1 << 60) - 1
+        sc = ShardedCommitter(ctx, m, k, rho, rank, world, pipeline, sub)
+        dev = sc.dev
+        msg = matrix_rows_torch(seed, sc.row_ids, k, dev) if sc.rows_g else torch.zeros((k, 4), dtype=torch.int64, device=dev)
         for _ in range(args.warmup):
             sc.commit_async(msg)
         root0 = sc.root()
+        if expected_root is not None:
+            assert root0.hex() == expected_root, f"root {root0.hex()} differs from the oracle-pinned {expected_root}"
         launches0 = ctx.launches
         dist.barrier()
         torch.cuda.synchronize()
@@ -318,14 +242,15 @@ class ShardedCommitter:
         launches = ctx.launches - launches0
         assert sc.root() == root0
         ms_per_step = float(ms.item()) / args.steps
-        marks = []
+        # one extra, untimed step with per-kernel events (phase marks on the context stream; the hash runs on its own)
         ctx.set_timing(True)
         ctx.phase_ms()
-        sc.commit_async(msg, marks)     # one extra, untimed step with per-phase and per-kernel events
+        sc.commit_async(msg)
         torch.cuda.synchronize()
-        kernel_ms = {p: v[0] / max(1, v[1]) for p, v in ctx.phase_ms().items() if v[1]}
+        phases = ctx.phase_ms()
+        kernel_ms = {p: v[0] for p, v in phases.items() if v[1]}
+        kernel_launches = {p: v[1] for p, v in phases.items() if v[1]}
         ctx.set_timing(False)
-        phase_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         value = R * k / (ms_per_step * 1e-3)
         # end to end: pinned host shard -> device, root back on the host, every step
         host = torch.empty_like(msg, device="cpu").pin_memory()
@@ -341,183 +266,70 @@ class ShardedCommitter:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         assert r == root0
         e2e_ms = float(dt.item()) * 1e3 / args.steps
+        rows_g = sc.rows_g
         sc.close()
-        par = (f"rows/{world} encode with the column exchange fused into the last NTT pass (NVLink peer stores) -> "
-               f"column-range/{world} hash + subtree -> NCCL root all-gather") if mode == "fused" else \
-              f"rows/{world} encode -> NCCL all-to-all -> column-range/{world} hash + subtree -> root all-gather"
+        par = (f"rows/{world} encode (4x{sub} row blocks) with the column exchange fused into the encode kernels (NVLink peer "
+               f"stores) -> column-range/{world} BLAKE2s of each block behind the encoding of the next -> subtree -> root "
+               f"exchange through peer mailboxes (device flags)")
         return {
             "metric": "fr_elems_per_s_encode_commit", "value": value, "unit": "Fr elems/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 Montgomery (BN254 Fr)", "data": "synthetic",
             "config": {"rows": R, "k": k, "n": rho * k, "rho_inv": rho, "parallelism": par,
-                       "l2_policy": "inputs larger than L2"},
+                       "l2_policy": "inputs larger than L2", "seed": seed},
             "e2e": {"value": R * k / (e2e_ms * 1e-3), "unit": "Fr elems/s", "h2d_bytes_per_step": int(msg.numel() * 8) * world,
                     "d2h_bytes_per_step": 32 * world, "ms_per_step": e2e_ms,
-                    "api": "ShardedCommitter.commit(host pinned row shard) -> root on host, per rank"},
-            "gpu_launches": int(launches), "root": root0.hex(), "phase_ms_rank0": phase_ms,
-            "kernel_ms_per_launch_rank0": kernel_ms, "rows_per_rank": sc.rows_g,
-            "hash_pipeline": bool(sc.pipeline),
+                    "api": "lg_shard_commit(host pinned row shard) -> root on host, per rank"},
+            "gpu_launches": int(launches), "root": root0.hex(),
+            "root_check": ("equals the CPU-oracle root of the whole matrix (tests/golden/full_size_root.json)"
+                           if expected_root is not None else "no pinned root for this shape"),
+            "kernel_ms_rank0": kernel_ms, "kernel_launches_rank0": kernel_launches, "rows_per_rank": rows_g,
+            "hash_pipeline": os.environ.get("LG_SHARD_PIPELINE", "1") != "0" if pipeline is None else bool(pipeline),
         }
 
 
 class ShardedProver:
-    """LigeroCircuit::prove over G GPUs (SURVEY 8e): the commitment is ShardedCommitter's; afterwards every rank
-    holds ALL rows of its column range, so the three tests are column-parallel with no partial sums to reduce:
+    """LigeroCircuit::prove over G GPUs (SURVEY 8e) -- lg_shard_prove / lg_shard_prove_matrix: the commitment is
+    ShardedCommitter's; afterwards every rank holds ALL rows of its column range, so the three tests are column-parallel
+    with no partial sums to reduce; the owner of an opened column serves it over NVLink together with the path inside
+    its subtree.  Every rank runs the same Fiat-Shamir transcript, so all ranks end with the same proof, byte-identical
+    to the single-GPU prover's (tests/test_gpu_multi.py) and through it to the oracle's."""
 
-      Test-Interleaved   r^T U_pre on the rank's columns                      -> all-gather of k/G values
-      Test-Linear        r_a = r^T A (replicated, O(nnz)); its 4m rows are extended to the odd points of the 2k
-                         domain row-sharded, with the same fused NVLink scatter as the witness (rho = 2, Montgomery
-                         form kept); q on the rank's 2k/G points               -> all-gather, one inverse NTT
-      Test-Quadratic     q on the rank's 2k/G points                           -> all-gather, one inverse NTT
-      openings           the owner of a column returns it with the path inside its subtree; the top log2(G)
-                         siblings come from the all-gathered subtree roots
-
-    Every rank runs the same Fiat-Shamir transcript on the gathered values, so all ranks end with the same proof,
-    byte-identical to the single-GPU (and the reference's) proof for the same witness and sponge."""
-
-    def __init__(self, ctx, ligero, rank: int, world: int):
-        from ctypes import byref, c_void_p
-        from .backend import check
+    def __init__(self, ctx, ligero, rank: int, world: int, sub_blocks: int = 1):
         self.ctx, self.L, self.rank, self.world = ctx, ligero, rank, world
         self.m, self.k, self.n, self.t = ligero.m, ligero.k, ligero.n, ligero.t
         self.rho = self.n // self.k
-        self.committer = ShardedCommitter(ctx, self.m, self.k, self.rho, rank, world, "fused")
-        c = self.committer
-        self.rows, self.kg = 4 * self.m, c.kg
-        self.rhat, self.rhat_ptrs, self._rhat_peers = open_peer_shards(ctx, self.rows, self.kg, 2, rank, world)
-        self.rhat_scratch = (torch.empty((max(c.rows_g, 1) * self.k, 4), dtype=torch.int64, device=c.dev)
-                             if self.k > 1024 else None)
-        self.row_ids = torch.tensor(local_row_ids(self.m, world, rank), dtype=torch.int64, device=c.dev)
-        a = c_void_p()
-        check(ctx.lib.lg_ligero_constraints(ligero.handle, byref(a)), ctx.handle, "lg_ligero_constraints")
-        self.a = a
-        dist.barrier()
+        self.committer = ShardedCommitter(ctx, self.m, self.k, self.rho, rank, world, None, sub_blocks, self.t)
+        self.rows = 4 * self.m
+        self.row_ids = torch.tensor(self.committer.row_ids, dtype=torch.int64, device=self.committer.dev)
 
     def close(self):
-        self.ctx.sync()
-        dist.barrier()
-        for p in self._rhat_peers:
-            self.ctx.lib.lg_ipc_close(self.ctx.handle, p)
-        self._rhat_peers = []
-        dist.barrier()
-        self.rhat.free()
         self.committer.close()
 
     def local_rows(self, preenc_u):
-        """this rank's rows [X_g; Y_g; Z_g; W_g] of a full 4m x k pre-encoding matrix (numpy or torch, [4mk, 4])"""
+        """this rank's rows (lg_shard_layout order) of a full 4m x k pre-encoding matrix (numpy or torch, [4mk, 4])"""
         full = torch.as_tensor(preenc_u.view("int64") if hasattr(preenc_u, "ctypes") else preenc_u)
         loc = full.view(self.rows, self.k, 4)[self.row_ids.to(full.device)].reshape(-1, 4).contiguous()
         return loc.to(self.committer.dev)
 
     def prove(self, var_assignment, sponge):
-        """LigeroCircuit::prove over G GPUs from the variable assignment alone: every rank runs the (cheap, replicated)
-        evaluation trace on its own GPU (lg_ligero_witness_matrix_dev), keeps its rows of [X;Y;Z;W] and goes on with
-        prove_matrix -- no host trace, no matrix upload."""
-        pre = self.L.witness_matrix_device(var_assignment)
-        return self.prove_matrix(self.local_rows(pre), sponge)
-
-    # -- collectives over host-sized results -------------------------------------------------------
-    def _gather(self, part_np):
         import numpy as np
-        t = torch.from_numpy(np.ascontiguousarray(part_np).view(np.int64)).to(self.committer.dev)
-        return gather_concat(t).cpu().numpy().view(np.uint64)
-
-    def _open(self, sponge, subtree_roots):
-        import numpy as np
-        dev, world, rank = self.committer.dev, self.world, self.rank
-        idx = self.ctx.expand_indices(sponge.squeeze_bytes(32), self.n, self.t)
-        where = split_openings(idx, self.n, world)
-        mine = [q for q, (h, _) in enumerate(where) if h == rank]
-        depth_local = (self.n // world).bit_length() - 2
-        cols_all = torch.zeros((self.t, self.rows, 4), dtype=torch.int64, device=dev)
-        sib_all = torch.zeros((self.t, 4), dtype=torch.int64, device=dev)
-        auth_all = torch.zeros((self.t, max(depth_local, 0) * 4 + 1), dtype=torch.int64, device=dev)
-        if mine:
-            cols, sib, auth = self.committer.mat_cols.open(np.array([where[q][1] for q in mine], dtype=np.uint64))
-            sel = torch.tensor(mine, dtype=torch.int64, device=dev)
-            cols_all[sel] = torch.from_numpy(cols.view(np.int64)).to(dev)
-            sib_all[sel] = torch.from_numpy(sib.view(np.int64).reshape(len(mine), 4)).to(dev)
-            if depth_local > 0:
-                auth_all[sel, : depth_local * 4] = torch.from_numpy(auth.view(np.int64).reshape(len(mine), depth_local * 4)).to(dev)
-        # exactly one rank contributes a non-zero row per opened column: the sum is a gather
-        for tns in (cols_all, sib_all, auth_all):
-            dist.all_reduce(tns)
-        top = top_auth_paths(subtree_roots)
-        cols_np = cols_all.cpu().numpy().view(np.uint64)
-        sib_np = sib_all.cpu().numpy().view(np.uint8).reshape(self.t, 32)
-        auth_loc = auth_all[:, : max(depth_local, 0) * 4].cpu().numpy().view(np.uint8).reshape(self.t, max(depth_local, 0), 32)
-        depth = self.n.bit_length() - 2
-        auth_np = np.zeros((self.t, depth, 32), dtype=np.uint8)
-        ntop = depth - max(depth_local, 0)
-        for q, (h, _) in enumerate(where):
-            for d in range(ntop):
-                auth_np[q, d] = np.frombuffer(top[h][d], dtype=np.uint8)
-            auth_np[q, ntop:] = auth_loc[q]
-        return cols_np, np.ascontiguousarray(idx, dtype=np.uint64), sib_np, auth_np
-
-    def prove_matrix(self, local_rows, sponge):
-        """local_rows: this rank's rows of the pre-encoding matrix (see local_rows()); returns a LigeroProof."""
-        import numpy as np
-        from ctypes import byref, c_size_t, c_void_p
+        from ctypes import byref, c_void_p
         from .api import LigeroProof
-        from .backend import _ptr, check
-        ctx, lib, c = self.ctx, self.ctx.lib, self.committer
-        root = c.commit(local_rows)                                            # mod.rs:521-551
-        r_host = c.roots.cpu().numpy()
-        subtree_roots = [bytes(r_host[g]) for g in range(self.world)]
-        sponge.absorb_bytes(root)                                              # 560
-        # Test-Interleaved (646-669)
-        r = ctx.expand_fr(sponge.squeeze_bytes(32), self.rows)
-        lc = self._gather(c.mat_cols.row_combine(r))                           # k x 4
-        sponge.absorb_fr(lc)
-        opened = [self._open(sponge, subtree_roots)]
-        # Test-Linear-Constraints (712-747)
-        seed = np.frombuffer(sponge.squeeze_bytes(32), dtype=np.uint8).copy()
-        r_a = torch.empty((self.rows * self.k, 4), dtype=torch.int64, device=c.dev)
-        check(lib.lg_linear_ra(ctx.handle, self.a, _ptr(seed), _ptr(r_a)), ctx.handle, "lg_linear_ra")
-        loc = r_a.view(self.rows, self.k, 4)[self.row_ids].reshape(-1, 4).contiguous() if c.m_g else None
-        with torch.cuda.stream(c.stream):
-            check(lib.lg_encode_sharded(ctx.handle, _ptr(loc) if loc is not None else None, c.m_g, self.k, 2, self.rhat_ptrs,
-                                        self.world, self.m, c.i0,
-                                        _ptr(self.rhat_scratch) if self.rhat_scratch is not None else None, 0),
-                  ctx.handle, "lg_encode_sharded(r_a)")
-            dist.all_reduce(c.flag)        # every rank's rows of r-hat have landed
-        ctx.sync()
-        base = int(lib.lg_matrix_u_dev(self.rhat.handle))
-        ev = np.empty((2 * self.kg, 4), dtype=np.uint64)
-        check(lib.lg_linear_evals(c.mat_cols.handle, c_void_p(base), c_void_p(base + self.rows * self.kg * 32), _ptr(ev)),
-              ctx.handle, "lg_linear_evals")
-        lin = self._poly(self._gather(ev))
-        sponge.absorb_fr(lin)
-        opened.append(self._open(sponge, subtree_roots))
-        # Test-Quadratic-Constraints (832-859)
-        rq = ctx.expand_fr(sponge.squeeze_bytes(32), self.m)
-        check(lib.lg_quadratic_evals(c.mat_cols.handle, _ptr(rq), _ptr(ev)), ctx.handle, "lg_quadratic_evals")
-        quad = self._poly(self._gather(ev))
-        sponge.absorb_fr(quad)
-        opened.append(self._open(sponge, subtree_roots))
-        # LigeroProof
-        depth = self.n.bit_length() - 2
-        arr = lambda j: (c_void_p * 3)(*[_ptr(o[j]).value for o in opened])
-        rootb = np.frombuffer(root, dtype=np.uint8).copy()
+        from .backend import _ptr, check, fr_to_limbs
+        idx = np.array([i for i, _ in var_assignment], dtype=np.uint64)
+        vals = fr_to_limbs([v for _, v in var_assignment])
         h = c_void_p()
-        check(lib.lg_proof_assemble(_ptr(rootb), _ptr(lc), self.k, _ptr(lin), len(lin), _ptr(quad), len(quad), self.t, self.rows,
-                                    depth, arr(0), arr(1), arr(2), arr(3), byref(h)), ctx.handle, "lg_proof_assemble")
+        check(self.ctx.lib.lg_shard_prove(self.committer.handle, self.L.handle, _ptr(idx), _ptr(vals), len(idx), 1, sponge.handle,
+                                          byref(h)), self.ctx.handle, "lg_shard_prove")
         return LigeroProof(h)
 
-    def _poly(self, evals_np):
-        import numpy as np
-        from ctypes import byref, c_size_t
+    def prove_matrix(self, local_rows, sponge):
+        from ctypes import byref, c_void_p
+        from .api import LigeroProof
         from .backend import _ptr, check
-        out = np.empty((2 * self.k, 4), dtype=np.uint64)
-        n = c_size_t()
-        check(self.ctx.lib.lg_poly_from_evals(self.ctx.handle, _ptr(np.ascontiguousarray(evals_np)), 2 * self.k, _ptr(out), byref(n)),
-              self.ctx.handle, "lg_poly_from_evals")
-        return np.ascontiguousarray(out[: n.value])
-
-
-class _DevBytes:
-    """__cuda_array_interface__ view of raw device memory (library-owned), for torch interop."""
-
-    def __init__(self, ptr: int, nbytes: int, device: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+        h = c_void_p()
+        check(self.ctx.lib.lg_shard_prove_matrix(self.committer.handle, self.L.handle,
+                                                 _ptr(local_rows) if self.committer.rows_g else None, sponge.handle, byref(h)),
+              self.ctx.handle, "lg_shard_prove_matrix")
+        return LigeroProof(h)
