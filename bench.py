@@ -3,6 +3,7 @@
 Merkle tree) for the 2^24-gate synthetic-circuit witness matrix, in Fr elements/s encoded.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log-gates G]
+    python bench.py --workload micro --rows R --n N --rho-inv 4        (BASELINE config 5, one grid point)
 
 One "step" = one full encode+commit of the R x k pre-encoding matrix (R = 4m rows, k columns,
 n = 8k codeword length; shapes from src/ligero/mod.rs:171-175, 275-294 of the reference).
@@ -40,8 +41,46 @@ def shape_for_gates(log_gates: int):
     return 4 * m, k, RHO_INV * k, m
 
 
-def workload_name(log_gates, R, k, n):
-    return f"synthetic 2^{log_gates}-gate circuit witness matrix: {R}x{k} -> {R}x{n} (rho_inv=8), dense uniform Fr"
+SEED = 20240          # ligero_b200/synthetic.py: every element is a function of (SEED, row, column) only
+
+
+def workload_name(log_gates, R, k, n, rho=RHO_INV):
+    if log_gates is None:
+        return (f"isolated RS-encode + Merkle-commit microbenchmark: {R}x{k} -> {R}x{n} (rho_inv={rho}), "
+                f"pseudo-random Fr (splitmix64 limbs, every element < r)")
+    return (f"synthetic 2^{log_gates}-gate circuit witness matrix: {R}x{k} -> {R}x{n} (rho_inv={rho}), "
+            f"pseudo-random Fr (splitmix64 limbs, every element < r)")
+
+
+def pinned_root(log_gates, seed=SEED):
+    """root of the WHOLE matrix computed by the CPU oracle (scripts/pin_full_size_root.py), or None"""
+    p = os.path.join(ROOT, "tests", "golden", "full_size_root.json")
+    try:
+        return json.load(open(p)).get(f"2^{log_gates}/seed{seed}", {}).get("root")
+    except Exception:
+        return None
+
+
+def executed_products(R, k, rho):
+    """Fr multiplications the encode kernels ISSUE for one R x k -> R x rho*k encode (ntt.cu): per 1024-element chunk
+    the persistent kernel does 4352 (inverse tail) + (rho-1) * 5376 (scale + forward stages 0-9; unit twiddles are skipped
+    only where a whole warp skips them), and every strided stage st >= 10 skips its k / 2^(st+1) unit twiddles per row."""
+    q = k.bit_length() - 1
+    if q < 10:
+        return R * ((k // 2) * q + (rho - 1) * ((k // 2) * q + k))
+    strided = sum(k // 2 - (k >> (st + 1)) for st in range(10, q))
+    return R * ((k >> 10) * (4352 + (rho - 1) * 5376) + rho * strided)
+
+
+def resolve_shape(args):
+    """(R, k, n, m, rho_inv, log_gates or None)"""
+    if args.workload == "micro":
+        rho = args.rho_inv or 4
+        assert args.rows % 4 == 0 and args.n % rho == 0
+        return args.rows, args.n // rho, args.n, args.rows // 4, rho, None
+    R, k, n, m = shape_for_gates(args.log_gates)
+    rho = args.rho_inv or RHO_INV
+    return R, k, rho * k, m, rho, args.log_gates
 
 
 def measured_peaks():
@@ -62,8 +101,12 @@ def ncu_traffic(kernel: str, R: int, k: int):
     best = None
     pdir = os.path.join(ROOT, "profiles")
     try:
+        # only captures of the CURRENT build count: this round's files, and the kernel must exist in the loaded library
+        from ligero_b200 import LIB_PATH
+        if kernel.encode() not in open(LIB_PATH, "rb").read():
+            return None
         for name in sorted(os.listdir(pdir)):
-            if not (name.endswith(".jsonl") and "ncu_full" in name):
+            if not (name.endswith(".jsonl") and "ncu_full" in name and name.startswith("r2")):
                 continue
             for line in open(os.path.join(pdir, name)):
                 if not line.startswith("{"):
@@ -122,7 +165,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None}
 
 
-def cpu_port_throughput(k: int, seconds_budget: float = 12.0, threads: int = 0):
+def cpu_port_throughput(k: int, seconds_budget: float = 12.0, threads: int = 0, rho: int = RHO_INV):
     """Time the CPU restatement (reference schedule) on a bounded row sample of the same workload."""
     import numpy as np
     from oracle import cref
@@ -131,11 +174,11 @@ def cpu_port_throughput(k: int, seconds_budget: float = 12.0, threads: int = 0):
     rows = max(threads, 8)
     total_rows, total_s = 0, 0.0
     sample = None
+    from ligero_b200.synthetic import matrix_rows_np
     for _ in range(4):
-        a = rng.integers(0, 2 ** 62, size=(rows * k, 4), dtype=np.uint64)
-        a[:, 3] &= (1 << 60) - 1
+        a = matrix_rows_np(SEED, range(rows), k)
         t0 = time.perf_counter()
-        cref.commit(a, rows, k, RHO_INV, threads=threads)
+        cref.commit(a, rows, k, rho, threads=threads)
         dt = time.perf_counter() - t0
         sample = (rows, dt)
         total_rows, total_s = rows, dt
@@ -150,23 +193,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    R, k, n, m = shape_for_gates(args.log_gates)
+    R, k, n, m, rho, log_gates = resolve_shape(args)
     import numpy as np
     from oracle import cref
     threads = os.cpu_count() or 1
     # size each step to ~ (120 s / steps) of CPU work using a short probe
-    tput, rows_p, secs_p, _ = cpu_port_throughput(k, seconds_budget=6.0, threads=threads)
+    tput, rows_p, secs_p, _ = cpu_port_throughput(k, seconds_budget=6.0, threads=threads, rho=rho)
     per_row = secs_p / rows_p
     budget = 150.0 / max(1, args.steps + args.warmup)
     rows = int(max(threads, min(R, budget / per_row)))
-    rng = np.random.default_rng(7)
-    a = rng.integers(0, 2 ** 62, size=(rows * k, 4), dtype=np.uint64)
-    a[:, 3] &= (1 << 60) - 1
+    from ligero_b200.synthetic import matrix_rows_np
+    a = matrix_rows_np(SEED, range(rows), k)
     for _ in range(args.warmup):
-        cref.commit(a, rows, k, RHO_INV, threads=threads)
+        cref.commit(a, rows, k, rho, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cref.commit(a, rows, k, RHO_INV, threads=threads)
+        cref.commit(a, rows, k, rho, threads=threads)
     dt = time.perf_counter() - t0
     value = rows * k * args.steps / dt
     sample = f"{rows} of {R} rows x k={k} (n={n}) per step, {args.steps} steps, reference schedule (iFFT_k + zero-padded FFT_n per row, transpose, BLAKE2s per column, SHA-256 tree)"
@@ -174,7 +216,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (R / rows), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 Montgomery (BN254 Fr)", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_gates, R, k, n), "rows": R, "k": k, "n": n,
+        "config": {"workload": workload_name(log_gates, R, k, n, rho), "rows": R, "k": k, "n": n, "rho_inv": rho,
                    "note": "ms_per_step is the sample time extrapolated linearly in rows to the full matrix"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -190,6 +232,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log-gates", type=int, default=24)
+    ap.add_argument("--workload", default="circuit", choices=["circuit", "micro"],
+                    help="circuit: the 2^log-gates witness-matrix shape (headline); micro: BASELINE config 5, one point of the "
+                         "isolated encode+commit grid given by --rows/--n/--rho-inv")
+    ap.add_argument("--rows", type=int, default=1 << 14)
+    ap.add_argument("--n", type=int, default=1 << 16)
+    ap.add_argument("--rho-inv", type=int, default=0, help="default 8 (circuit) / 4 (micro)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--prove-log-gates", type=int, nargs="*", default=[20, 24],
@@ -215,25 +263,26 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    R, k, n, m = shape_for_gates(args.log_gates)
+    R, k, n, m, rho, log_gates = resolve_shape(args)
     ctx = Context(local_rank)
     peaks, peak_kind = measured_peaks()
+    want_root = pinned_root(log_gates) if log_gates is not None and rho == RHO_INV else None
 
     if world > 1:
         from ligero_b200.parallel import ShardedCommitter
         sampler = ClockSampler(local_rank)
         sampler.start()
-        result = ShardedCommitter.bench(ctx, R, k, RHO_INV, args, rank, world)
+        result = ShardedCommitter.bench(ctx, R, k, rho, args, rank, world, SEED, want_root)
         clocks = sampler.stop()
         if rank == 0:
-            result["config"]["workload"] = workload_name(args.log_gates, R, k, n)
+            result["config"]["workload"] = workload_name(log_gates, R, k, n, rho)
             result["clocks"] = clocks
-            # dominant kernel on one rank: the shared-memory NTT over this rank's rows (same definition as N = 1)
-            kms = result.get("kernel_ms_per_launch_rank0", {})
+            # dominant kernel on one rank: the shared-memory NTT over this rank's rows (same definition as N = 1);
+            # kernel_ms_rank0 is the SUM over the launches of one step (one per row block)
+            kms = result.get("kernel_ms_rank0", {})
             rows_g = result.get("rows_per_rank", R // world)
-            blocks = 4 if result.get("hash_pipeline") else 1     # the block pipeline launches it once per row block
             if kms.get("ntt_local"):
-                gbs = 32.0 * (rows_g / blocks) * k * RHO_INV / (kms["ntt_local"] * 1e-3) / 1e9
+                gbs = 32.0 * rows_g * k * rho / (kms["ntt_local"] * 1e-3) / 1e9
                 hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
                 result["roofline"] = {
                     "bound": "hbm", "kernel": "ntt_local_kernel (rank 0)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -246,13 +295,13 @@ def main():
         return
 
     # ---------------- single GPU ----------------
-    g = torch.Generator(device="cuda")
-    g.manual_seed(20240 + rank)
-    msg = torch.randint(0, 2 ** 62, (R * k, 4), dtype=torch.int64, device="cuda", generator=g)
-    msg[:, 3] &= (1 << 60) - 1            # every element < r (top limb < 2^60)
+    from ligero_b200.synthetic import matrix_rows_torch
+    msg = matrix_rows_torch(SEED, range(R), k, "cuda")      # the same matrix every rank count encodes
     stream = torch.cuda.ExternalStream(ctx.stream)
-    cm = ctx.commit(msg, R, k, RHO_INV)   # allocates U / leaves / tree once (not timed)
+    cm = ctx.commit(msg, R, k, rho)       # allocates U / leaves / tree once (not timed)
     root0 = cm.root
+    if want_root is not None:
+        assert root0.hex() == want_root, f"root {root0.hex()} differs from the oracle-pinned {want_root}"
 
     def step_device():
         check(ctx.lib.lg_recommit(cm.handle, _ptr(msg), None), ctx.handle, "lg_recommit")
@@ -268,12 +317,26 @@ def main():
     launches0 = ctx.launches
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    total_ms = e0.elapsed_time(e1)
+    small = R * n * 32 <= (256 << 20)        # working set could stay in the 126 MB L2: flush it between timed steps
+    if small:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        total_ms = 0.0
+        with torch.cuda.stream(stream):
+            for _ in range(args.steps):
+                flush.zero_()                # 256 MiB of writes on the context stream, outside the timed interval
+                e0.record(stream)
+                step_device()
+                e1.record(stream)
+                e1.synchronize()
+                total_ms += e0.elapsed_time(e1)
+        del flush
+    else:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
     phases = ctx.phase_ms()
     ctx.set_timing(False)
@@ -282,35 +345,54 @@ def main():
     ms_per_step = total_ms / args.steps
     value = R * k / (ms_per_step * 1e-3)
 
-    # dominant kernel: the shared-memory NTT (iNTT tail + 7 coset NTTs): reads R*k, writes 7*R*k elements
+    # dominant kernel: the shared-memory NTT (iNTT tail + rho-1 coset NTTs): reads R*k, writes (rho-1)*R*k elements
     local_ms, local_cnt = phases["ntt_local"]
     local_ms_per_launch = local_ms / max(1, local_cnt)
-    local_bytes = 32.0 * R * k * RHO_INV
+    local_bytes = 32.0 * R * k * rho
     achieved_gbs = local_bytes / (local_ms_per_launch * 1e-3) / 1e9
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # integer roofline: Fr multiplications actually required by the encode schedule
+    local_kernel = "ntt_persist_kernel" if k >= 1024 else "ntt_local_kernel"
+    # integer roofline, SURVEY 8(d):  T_bound = max(W_mac / P_int, B_alg / BW_hbm),  frac = T_bound / T_measured
+    #   W_mul   Fr multiplications of the schedule (algorithmic, unit twiddles included)
+    #   W_mac   SURVEY's 32-bit MAC count for a CIOS implementation: 136 per product + 72 per codeword element converted
+    #   P_int   measured rate of the multiplier's own instruction (IMAD.WIDE.U32[.X] in carry chains), lg_bench_int_peak
+    # The kernels need fewer MACs than CIOS (table-constant Shoup products: 99 wide + 16 low multiplies, and no
+    # Montgomery->canonical conversion at all), so the SURVEY-formula fraction can exceed 1; the fraction that is a true
+    # bound divides the wide-multiply issue time of the products the kernels EXECUTE by the measured time.
     logk = k.bit_length() - 1
-    w_mul = R * ((k // 2) * logk + (RHO_INV - 1) * ((k // 2) * logk + k))
+    w_mul = R * ((k // 2) * logk + (rho - 1) * ((k // 2) * logk + k))
+    w_mac = 136.0 * w_mul + 72.0 * R * n
+    w_exec = executed_products(R, k, rho)
+    w_mac_exec = w_exec * (99 + 16 * 0.5)          # a low multiply (IMAD) holds the pipe half as long as a wide one
+    p_int = int_peak["imad_wide_per_s"]
     enc_ms = sum(phases[p][0] for p in ("ntt_strided_inv", "ntt_local", "ntt_strided_fwd")) / args.steps
     step_bytes = 32.0 * R * (k + 2 * n) + 64.0 * n
+    t_hbm_ms = step_bytes / (hbm_peak * 1e9) * 1e3
+    t_int_survey_ms = w_mac / p_int * 1e3
+    t_int_exec_ms = w_mac_exec / p_int * 1e3
     roofline = {
-        "bound": "hbm", "kernel": "ntt_local_kernel", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved_gbs / hbm_peak, "traffic": ncu_traffic("ntt_local_kernel", R, k),
+        "bound": "hbm", "kernel": local_kernel, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": achieved_gbs / hbm_peak, "traffic": ncu_traffic(local_kernel, R, k),
         "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-        "note": "multi-limb modular arithmetic is integer-pipe bound, not HBM bound (north_star): see int_roofline",
+        "note": "HBM view of the dominant kernel, as the contract asks; the BINDING bound of this path is the integer "
+                "multiplier (north_star: multi-limb modular arithmetic), see int_roofline",
         "int_roofline": {
-            "bound": "int (issue port: IMAD.WIDE.U32 holds an SM sub-partition's dispatch for 4 cycles, every other "
-                     "integer instruction for 1; one table-constant product = 100 wide + 16 low multiplies)",
-            "fr_mul_required_per_step": w_mul,
-            "achieved_fr_mul_per_s": w_mul / (enc_ms * 1e-3),
-            "peak_butterfly_per_s": int_peak["butterfly_per_s"],
-            "peak_shoup_mul_per_s": int_peak["shoup_mul_per_s"],
-            "peak_montgomery_mul_per_s": int_peak["fr_mul_per_s"],
-            "frac": (w_mul / (enc_ms * 1e-3)) / int_peak["butterfly_per_s"],
-            "peak_source": "lg_bench_int_peak, measured in this run at 2048 threads/SM: chains of whole lazily reduced "
-                           "butterflies (the denominator), of bare table-constant products, and of Montgomery products "
-                           "(round-1 multiplier, for comparison)",
-            "encode_ms_per_step": enc_ms,
+            "bound": "int: IMAD.WIDE.U32(.X) issue on the FMA-heavy pipe (4 cycles per warp instruction and SM sub-partition)",
+            "W_mul": w_mul, "W_mac": w_mac, "imad_wide_per_s": p_int,
+            "T_bound_ms": max(t_int_survey_ms, t_hbm_ms), "T_int_ms": t_int_survey_ms, "T_hbm_ms": t_hbm_ms,
+            "T_measured_ms": ms_per_step, "frac_survey_formula": max(t_int_survey_ms, t_hbm_ms) / ms_per_step,
+            "executed": {"fr_mul_per_step": w_exec, "wide_mac_equiv_per_product": 107, "W_mac": w_mac_exec,
+                         "T_int_ms": t_int_exec_ms, "encode_ms_per_step": enc_ms, "frac": t_int_exec_ms / enc_ms},
+            "frac": t_int_exec_ms / enc_ms,
+            "which_is_the_bound": "frac = issue time of the wide multiplies the three NTT kernels execute / their measured "
+                                  "time (<= 1 by construction; ncu sm__pipe_fmaheavy_cycles_active of the same kernels is "
+                                  "the independent reading, profiles/r2_*).  frac_survey_formula uses SURVEY 8(d)'s CIOS MAC "
+                                  "count over the whole step and exceeds what any CIOS kernel could reach because this "
+                                  "schedule issues ~25 % fewer MACs per product and converts nothing for hashing.",
+            "other_peaks": {"butterfly_per_s": int_peak["butterfly_per_s"], "shoup_mul_per_s": int_peak["shoup_mul_per_s"],
+                            "montgomery_mul_per_s": int_peak["fr_mul_per_s"]},
+            "peak_source": "lg_bench_int_peak in this run, 2048 threads/SM: 32 independent carry chains of two wide "
+                           "multiplies per thread and iteration, multiplicands rewritten every iteration",
         },
         "step_hbm": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_per_step * 1e-3) / 1e9},
         "phase_ms_per_step": {p: v[0] / args.steps for p, v in phases.items() if v[1]},
@@ -321,7 +403,9 @@ def main():
     # the encoder short-circuits them (bit-exact).  Not the headline: `value` above is dense data.
     witness_shaped = None
     try:
-        sol_len = (1 << args.log_gates) + 4
+        if log_gates is None:
+            raise RuntimeError("not a circuit shape")
+        sol_len = (1 << log_gates) + 4
         data_rows = -(-sol_len // k)
         wmsg = msg.clone().view(4, m, k, 4)
         wmsg[:, data_rows:] = 0
@@ -365,7 +449,7 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        v, rows_s, secs, thr = cpu_port_throughput(k)
+        v, rows_s, secs, thr = cpu_port_throughput(k, rho=rho)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": thr, "kind": "port",
                         "sample": f"{rows_s} of {R} rows x k={k} (n={n}), reference schedule, {secs:.1f} s"}
 
@@ -377,7 +461,7 @@ def main():
         del msg
         torch.cuda.empty_cache()
         import ligero_b200 as lb
-        for lg in args.prove_log_gates:
+        for lg in (args.prove_log_gates if args.workload == "circuit" else []):
             circ, out, assign = lb.ArithmeticCircuit.synthetic(1 << lg, 2024)
             lc = lb.LigeroCircuit(ctx, circ, [out])
             lc.prove(assign, lb.PoseidonSponge.test_sponge())          # allocates the resident buffers
@@ -406,10 +490,15 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32x8 Montgomery (BN254 Fr)", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_gates, R, k, n), "rows": R, "k": k, "n": n, "rho_inv": RHO_INV,
-                   "l2_policy": "inputs larger than L2 (4 GiB matrix, 32 GiB codeword matrix per step)",
-                   "codeword_elems_per_s": value * RHO_INV, "witness_shaped": witness_shaped,
+        "config": {"workload": workload_name(log_gates, R, k, n, rho), "rows": R, "k": k, "n": n, "rho_inv": rho, "seed": SEED,
+                   "l2_policy": (f"inputs larger than L2 ({R * k * 32 / 2**30:.2f} GiB matrix, {R * n * 32 / 2**30:.1f} GiB codeword "
+                                 f"matrix per step)" if R * n * 32 > (256 << 20) else
+                                 "L2 flushed (256 MiB of writes) before every timed step; each step timed with its own events"),
+                   "codeword_elems_per_s": value * rho, "witness_shaped": witness_shaped,
                    "whole_prove": prove_info},
+        "root": root0.hex(),
+        "root_check": ("equals the CPU-oracle root of the whole matrix (tests/golden/full_size_root.json)"
+                       if want_root is not None else "no pinned root for this shape"),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

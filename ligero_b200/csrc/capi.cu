@@ -133,25 +133,40 @@ __global__ void __launch_bounds__(256) bench_fr_shoup_kernel(Fr* io, int iters) 
   io[t] = fr_add(fr_add(fr_normalize(a), fr_normalize(b)), fr_add(fr_normalize(c), fr_normalize(d)));
 }
 
+// Raw rate of the multiplier's own instruction: 32x32->64 multiply-accumulates in the carry-chained form the Shoup body
+// issues (mad.lo.cc / madc.hi.cc / madc.lo.cc / madc.hi -> IMAD.WIDE.U32 + IMAD.WIDE.U32.X), 32 independent chains of two
+// per thread and iteration (64 wide multiplies), multiplicands rewritten every iteration so that nothing is loop
+// invariant (ptxas hoists invariant products: the round-1 probe measured 64-bit additions).  2048 threads per SM.
 __global__ void __launch_bounds__(256) bench_imad_wide_kernel(uint64_t* io, int iters) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t a0 = io[t], a1 = a0 ^ 0x9e3779b97f4a7c15ull, a2 = a0 + 12345, a3 = ~a0;
-  uint64_t a4 = a0 * 3, a5 = a0 * 5, a6 = a0 * 7, a7 = a0 * 11;
-  const uint32_t m = (uint32_t)t | 1u;
-  for (int i = 0; i < iters; i++) {
+  uint32_t a[8], b[8], lo[8], hi[8];
+  const uint64_t s0 = io[t];
 #pragma unroll
-    for (int u = 0; u < 8; u++) {  // 8 independent chains x 8 = 64 mad.wide per iteration
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"((uint32_t)a0), "r"(m));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"((uint32_t)a1), "r"(m));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"((uint32_t)a2), "r"(m));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"((uint32_t)a3), "r"(m));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"((uint32_t)a4), "r"(m));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"((uint32_t)a5), "r"(m));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"((uint32_t)a6), "r"(m));
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"((uint32_t)a7), "r"(m));
+  for (int i = 0; i < 8; i++) {
+    a[i] = (uint32_t)(s0 >> i) * 2654435761u + i;
+    b[i] = (uint32_t)(s0 >> (i + 8)) * 40503u + 7 * i + 1;
+    lo[i] = (uint32_t)s0 + i;
+    hi[i] = (uint32_t)(s0 >> 32) ^ i;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2)
+        asm volatile("mad.lo.cc.u32 %0, %4, %5, %0; madc.hi.cc.u32 %1, %4, %5, %1; madc.lo.cc.u32 %2, %4, %6, %2; madc.hi.u32 %3, %4, %6, %3;"
+                     : "+r"(lo[i]), "+r"(hi[i]), "+r"(lo[i + 1]), "+r"(hi[i + 1])
+                     : "r"(a[j]), "r"(b[i]), "r"(b[i + 1]));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {  // 16 ALU-pipe instructions per 64 multiplies
+      a[i] ^= hi[i];
+      b[i] += lo[(i + 3) & 7];
     }
   }
-  io[t] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  uint64_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r += ((uint64_t)hi[i] << 32) + lo[i] + a[i] + b[i];
+  io[t] = r;
 }
 
 static int matrix_alloc(lg_ctx* ctx, size_t rows, size_t k, uint32_t rho_inv, lg_matrix** out, void* external_u = nullptr) {
@@ -902,7 +917,7 @@ int lg_bench_int_peak(lg_ctx* ctx, double ms_target, double* fr_mul_per_s, doubl
     }
     c->last_shoup_peak[which] = 4.0 * iters * (double)nthreads / (ms * 1e-3);
   }
-  // raw IMAD.WIDE.U32
+  // raw IMAD.WIDE.U32(.X) in the multiplier's carry-chained form
   iters = 64;
   for (int rep = 0; rep < 3; rep++) {
     cudaEventRecord(e0, c->stream);

@@ -704,7 +704,7 @@ int lg_circuit_free(lg_circuit* c) {
 }
 const char* lg_circuit_last_error(const lg_circuit* c) { return c ? c->error.c_str() : "null circuit"; }
 
-int lg_circuit_constant(lg_circuit* c, const uint64_t value[4], size_t* index_out) {  // mod.rs:76-84
+static int lg_circuit_constant_impl(lg_circuit* c, const uint64_t value[4], size_t* index_out) {  // mod.rs:76-84
   if (!c || !value) return ERR_INVALID;
   Fq v;
   memcpy(v.l, value, 32);
@@ -720,8 +720,11 @@ int lg_circuit_constant(lg_circuit* c, const uint64_t value[4], size_t* index_ou
   if (index_out) *index_out = idx;
   return OK;
 }
+int lg_circuit_constant(lg_circuit* c, const uint64_t value[4], size_t* index_out) {
+  return lg::guard([&]() { return lg_circuit_constant_impl(c, value, index_out); });
+}
 
-int lg_circuit_new_variable(lg_circuit* c, const char* label, size_t* index_out) {  // mod.rs:92-109
+static int lg_circuit_new_variable_impl(lg_circuit* c, const char* label, size_t* index_out) {  // mod.rs:92-109
   if (!c) return ERR_INVALID;
   const std::string lab = label ? std::string(label) : "var_" + std::to_string(c->variables.size());
   if (c->variables.count(lab)) {
@@ -733,6 +736,9 @@ int lg_circuit_new_variable(lg_circuit* c, const char* label, size_t* index_out)
   c->variables[lab] = idx;
   if (index_out) *index_out = idx;
   return OK;
+}
+int lg_circuit_new_variable(lg_circuit* c, const char* label, size_t* index_out) {
+  return lg::guard([&]() { return lg_circuit_new_variable_impl(c, label, index_out); });
 }
 
 int lg_circuit_get_variable(const lg_circuit* c, const char* label, size_t* index_out) {
@@ -780,7 +786,7 @@ int lg_circuit_node(const lg_circuit* c, size_t index, int* type, size_t* left, 
 }
 
 // evaluation_trace_multioutput + evaluate_multioutput (mod.rs:325-400): values of the output nodes
-int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
+static int lg_circuit_evaluate_impl(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
                         size_t n_outputs, uint64_t* out_vals, size_t* n_values_out) {
   if (!c || (n_vars && (!var_idx || !var_vals)) || !outputs || !out_vals) return ERR_INVALID;
   std::vector<std::pair<size_t, Fq>> vars(n_vars);
@@ -806,10 +812,14 @@ int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64
   if (n_values_out) *n_values_out = sorted.size();
   return OK;
 }
+int lg_circuit_evaluate(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
+                        size_t n_outputs, uint64_t* out_vals, size_t* n_values_out) {
+  return lg::guard([&]() { return lg_circuit_evaluate_impl(c, var_idx, var_vals, n_vars, outputs, n_outputs, out_vals, n_values_out); });
+}
 
 // from_constraint_system (mod.rs:455-520).  Matrices as ConstraintSystem::to_matrices yields them: CSR with
 // coefficient Fr values and column indices (column 0 = the constant one), n_cols = instance + witness variables.
-int lg_circuit_from_r1cs(size_t n_constraints, size_t n_cols, const uint64_t* const row_ptr[3], const uint64_t* const col_idx[3],
+static int lg_circuit_from_r1cs_impl(size_t n_constraints, size_t n_cols, const uint64_t* const row_ptr[3], const uint64_t* const col_idx[3],
                          const uint64_t* const coeffs[3], lg_circuit** out, size_t* outputs) {
   if (!out || !outputs || !row_ptr || !col_idx || !coeffs || n_cols == 0) return ERR_INVALID;
   lg_circuit* c = new (std::nothrow) lg_circuit();
@@ -863,12 +873,16 @@ int lg_circuit_from_r1cs(size_t n_constraints, size_t n_cols, const uint64_t* co
   *out = c;
   return OK;
 }
+int lg_circuit_from_r1cs(size_t n_constraints, size_t n_cols, const uint64_t* const row_ptr[3], const uint64_t* const col_idx[3],
+                         const uint64_t* const coeffs[3], lg_circuit** out, size_t* outputs) {
+  return lg::guard([&]() { return lg_circuit_from_r1cs_impl(n_constraints, n_cols, row_ptr, col_idx, coeffs, out, outputs); });
+}
 
 // read_constraint_system's R1CS half (src/reader.rs:6-19): the iden3 .r1cs v1 container -> the three
 // matrices as ConstraintSystem::to_matrices yields them (terms of a row merged per wire, zero coefficients dropped, wires
 // ascending, as ark-relations' sorted LinearCombination does) -> from_constraint_system.  The witness half of the
 // reference (a wasm witness calculator run by ark-circom) is out of scope: callers pass the assignment.
-int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out, size_t* outputs, size_t outputs_cap,
+static int lg_circuit_from_r1cs_bytes_impl(const uint8_t* data, size_t len, lg_circuit** out, size_t* outputs, size_t outputs_cap,
                                size_t* n_constraints_out, size_t* n_wires_out) {
   if (!data || !out) return ERR_INVALID;
   auto rd32 = [&](size_t off, uint32_t& v) {
@@ -883,7 +897,8 @@ int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out
   };
   uint32_t version = 0, nsec = 0;
   if (len < 12 || memcmp(data, "r1cs", 4) != 0 || !rd32(4, version) || !rd32(8, nsec) || version != 1) return ERR_INVALID;
-  size_t off = 12, hdr_off = 0, hdr_len = 0, body_off = 0, body_len = 0;
+  size_t off = 12, hdr_off = 0, hdr_len = 0, body_off = 0, body_len = 0, map_len = 0;
+  bool have_map = false;
   for (uint32_t sct = 0; sct < nsec; sct++) {
     uint32_t typ;
     uint64_t size;
@@ -895,6 +910,9 @@ int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out
     } else if (typ == 2) {
       body_off = off;
       body_len = size;
+    } else if (typ == 3) {  // wire -> label map: 8 bytes per wire
+      have_map = true;
+      map_len = size;
     }
     off += size;
   }
@@ -905,6 +923,10 @@ int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out
   rd32(hdr_off + 4 + 32, n_wires);
   rd32(hdr_off + 4 + 32 + 16 + 8, n_constraints);
   if (n_wires == 0 || n_constraints == 0) return ERR_INVALID;
+  // every count that drives an allocation must be justified by the file: a constraint takes at least 12 bytes of the
+  // body, and a wire 8 bytes of the wire-to-label section (files without that section: one byte of file per wire)
+  if ((size_t)n_constraints > body_len / 12) return ERR_INVALID;
+  if ((size_t)n_wires > (have_map ? map_len / 8 : len)) return ERR_INVALID;
   std::vector<uint64_t> row_ptr[3], col_idx[3];
   std::vector<Fq> coeff[3];
   size_t o = body_off;
@@ -945,13 +967,17 @@ int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out
   const uint64_t* cf[3] = {(const uint64_t*)coeff[0].data(), (const uint64_t*)coeff[1].data(), (const uint64_t*)coeff[2].data()};
   return lg_circuit_from_r1cs(n_constraints, n_wires, rp, ci, cf, out, outputs);
 }
+int lg_circuit_from_r1cs_bytes(const uint8_t* data, size_t len, lg_circuit** out, size_t* outputs, size_t outputs_cap,
+                               size_t* n_constraints_out, size_t* n_wires_out) {
+  return lg::guard([&]() { return lg_circuit_from_r1cs_bytes_impl(data, len, out, outputs, outputs_cap, n_constraints_out, n_wires_out); });
+}
 
 // Seeded random Add/Mul circuit of exactly `gates` gates for the synthetic configurations: two input
 // variables, gate type by a fair coin, operands drawn uniformly from all earlier non-constant nodes (depth O(log gates)
 // with overwhelming probability), every node feeds the single output, the output is an Add gate of value 1
 // (Add(sum, constant 1 - sum)), no gate has two constant operands.  sol_len of the LigeroCircuit is gates + 4.
 // Generator: splitmix64(seed); not part of the reference (its tests build circuits by hand).
-int lg_circuit_synthetic(size_t gates, uint64_t seed, lg_circuit** out, size_t* output, size_t var_idx[2], uint64_t var_vals[8]) {
+static int lg_circuit_synthetic_impl(size_t gates, uint64_t seed, lg_circuit** out, size_t* output, size_t var_idx[2], uint64_t var_vals[8]) {
   if (!out || !output || !var_idx || !var_vals || gates < 4) return ERR_INVALID;
   lg_circuit* c = new (std::nothrow) lg_circuit();
   if (!c) return ERR_NOMEM;
@@ -1027,11 +1053,14 @@ int lg_circuit_synthetic(size_t gates, uint64_t seed, lg_circuit** out, size_t* 
   *out = c;
   return OK;
 }
+int lg_circuit_synthetic(size_t gates, uint64_t seed, lg_circuit** out, size_t* output, size_t var_idx[2], uint64_t var_vals[8]) {
+  return lg::guard([&]() { return lg_circuit_synthetic_impl(gates, seed, out, output, var_idx, var_vals); });
+}
 
 // ---------------------------------------------------------------------------------------------------
 // sponge
 // ---------------------------------------------------------------------------------------------------
-int lg_sponge_new(int full_rounds, int partial_rounds, uint64_t alpha, const uint64_t* mds, const uint64_t* ark, int rate, int capacity,
+static int lg_sponge_new_impl(int full_rounds, int partial_rounds, uint64_t alpha, const uint64_t* mds, const uint64_t* ark, int rate, int capacity,
                   lg_sponge** out) {
   if (!out || !mds || !ark || rate < 1 || capacity < 0 || full_rounds < 0 || partial_rounds < 0) return ERR_INVALID;
   lgh::PoseidonConfig cfg;
@@ -1048,9 +1077,13 @@ int lg_sponge_new(int full_rounds, int partial_rounds, uint64_t alpha, const uin
   *out = new (std::nothrow) lg_sponge(cfg);
   return *out ? OK : ERR_NOMEM;
 }
+int lg_sponge_new(int full_rounds, int partial_rounds, uint64_t alpha, const uint64_t* mds, const uint64_t* ark, int rate, int capacity,
+                  lg_sponge** out) {
+  return lg::guard([&]() { return lg_sponge_new_impl(full_rounds, partial_rounds, alpha, mds, ark, rate, capacity, out); });
+}
 
 // ark_poly_commit::test_sponge() with the deterministic ark_std::test_rng() (ChaCha12 from the fixed seed)
-int lg_sponge_test(lg_sponge** out) {
+static int lg_sponge_test_impl(lg_sponge** out) {
   if (!out) return ERR_INVALID;
   const uint8_t seed[32] = {1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0};
   ChaChaRng rng(seed, 12);
@@ -1071,6 +1104,9 @@ int lg_sponge_test(lg_sponge** out) {
   *out = new (std::nothrow) lg_sponge(cfg);
   return *out ? OK : ERR_NOMEM;
 }
+int lg_sponge_test(lg_sponge** out) {
+  return lg::guard([&]() { return lg_sponge_test_impl(out); });
+}
 int lg_sponge_clone(const lg_sponge* s, lg_sponge** out) {
   if (!s || !out) return ERR_INVALID;
   *out = new (std::nothrow) lg_sponge(*s);
@@ -1080,29 +1116,38 @@ int lg_sponge_free(lg_sponge* s) {
   delete s;
   return OK;
 }
-int lg_sponge_absorb_bytes(lg_sponge* s, const uint8_t* data, size_t len) {
+static int lg_sponge_absorb_bytes_impl(lg_sponge* s, const uint8_t* data, size_t len) {
   if (!s || (!data && len)) return ERR_INVALID;
   s->s.absorb_bytes(data, len);
   return OK;
 }
-int lg_sponge_absorb_fr(lg_sponge* s, const uint64_t* elems, size_t count) {
+int lg_sponge_absorb_bytes(lg_sponge* s, const uint8_t* data, size_t len) {
+  return lg::guard([&]() { return lg_sponge_absorb_bytes_impl(s, data, len); });
+}
+static int lg_sponge_absorb_fr_impl(lg_sponge* s, const uint64_t* elems, size_t count) {
   if (!s || (!elems && count)) return ERR_INVALID;
   std::vector<Fq> v(count);
   memcpy(v.data(), elems, count * 32);
   s->s.absorb_field(v);
   return OK;
 }
-int lg_sponge_squeeze_bytes(lg_sponge* s, uint8_t* out, size_t len) {
+int lg_sponge_absorb_fr(lg_sponge* s, const uint64_t* elems, size_t count) {
+  return lg::guard([&]() { return lg_sponge_absorb_fr_impl(s, elems, count); });
+}
+static int lg_sponge_squeeze_bytes_impl(lg_sponge* s, uint8_t* out, size_t len) {
   if (!s || !out) return ERR_INVALID;
   const std::vector<uint8_t> b = s->s.squeeze_bytes(len);
   memcpy(out, b.data(), len);
   return OK;
 }
+int lg_sponge_squeeze_bytes(lg_sponge* s, uint8_t* out, size_t len) {
+  return lg::guard([&]() { return lg_sponge_squeeze_bytes_impl(s, out, len); });
+}
 
 // ---------------------------------------------------------------------------------------------------
 // LigeroCircuit
 // ---------------------------------------------------------------------------------------------------
-int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_ligero** out) {
+static int lg_ligero_new_impl(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_ligero** out) {
   if (!ctx || !circuit || !out || (!outputs && n_outputs)) return ERR_INVALID;
   if (circuit->nodes.empty()) return fail(ctx, ERR_INVALID, "empty circuit");
   lg_ligero* L = new (std::nothrow) lg_ligero();
@@ -1178,6 +1223,9 @@ int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs,
   *out = L;
   return OK;
 }
+int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_ligero** out) {
+  return lg::guard([&]() { return lg_ligero_new_impl(ctx, circuit, outputs, n_outputs, lambda, out); });
+}
 
 int lg_ligero_release_buffers(lg_ligero* L) {
   if (!L) return ERR_INVALID;
@@ -1224,7 +1272,7 @@ int lg_ligero_trace_info(const lg_ligero* L, size_t* gates, size_t* levels, size
 }
 
 // a1 on the device: evaluation trace by levels + scatter into [X;Y;Z;W], all in HBM (out_dev: Fr[4*m*k], device)
-int lg_ligero_witness_matrix_dev(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump,
+static int lg_ligero_witness_matrix_dev_impl(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump,
                                  uint64_t* out_dev) {
   if (!L || !out_dev || (n_vars && (!var_idx || !var_vals))) return ERR_INVALID;
   if (!lg::is_device_ptr(out_dev)) return fail(L->ctx, ERR_INVALID, "lg_ligero_witness_matrix_dev needs a device buffer");
@@ -1272,6 +1320,10 @@ int lg_ligero_witness_matrix_dev(lg_ligero* L, const size_t* var_idx, const uint
   }
   return s;
 }
+int lg_ligero_witness_matrix_dev(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump,
+                                 uint64_t* out_dev) {
+  return lg::guard([&]() { return lg_ligero_witness_matrix_dev_impl(L, var_idx, var_vals, n_vars, bump, out_dev); });
+}
 
 int lg_ligero_params(const lg_ligero* L, size_t* m, size_t* k, size_t* n, size_t* t, size_t* sol_len) {
   if (!L) return ERR_INVALID;
@@ -1284,7 +1336,7 @@ int lg_ligero_params(const lg_ligero* L, size_t* m, size_t* k, size_t* n, size_t
 }
 
 // the pre-encoding matrix [X;Y;Z;W] (mod.rs:476-516); out: Fr[4*m*k] host
-int lg_ligero_witness_matrix(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, uint64_t* out) {
+static int lg_ligero_witness_matrix_impl(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, uint64_t* out) {
   if (!L || !out || (n_vars && (!var_idx || !var_vals))) return ERR_INVALID;
   const lg_circuit& c = L->circuit;
   std::vector<std::pair<size_t, Fq>> vars(n_vars);
@@ -1320,9 +1372,12 @@ int lg_ligero_witness_matrix(lg_ligero* L, const size_t* var_idx, const uint64_t
   }
   return OK;
 }
+int lg_ligero_witness_matrix(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, uint64_t* out) {
+  return lg::guard([&]() { return lg_ligero_witness_matrix_impl(L, var_idx, var_vals, n_vars, bump, out); });
+}
 
 // prove_inner on a ready pre-encoding matrix (host or device): the commit-and-test transcript
-int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, lg_proof** out) {
+static int lg_prove_matrix_impl(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, lg_proof** out) {
   if (!L || !preenc_u || !sponge || !out) return ERR_INVALID;
   lg_ctx* ctx = L->ctx;
   lgh::PoseidonSponge& sp = sponge->s;
@@ -1392,9 +1447,12 @@ int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, l
   open_ms += lap();
   return done(OK);
 }
+int lg_prove_matrix(lg_ligero* L, const uint64_t* preenc_u, lg_sponge* sponge, lg_proof** out) {
+  return lg::guard([&]() { return lg_prove_matrix_impl(L, preenc_u, sponge, out); });
+}
 
 // LigeroCircuit::prove (bump = 1: indices refer to the caller's circuit) / prove_inner (bump = 0)
-int lg_prove(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out) {
+static int lg_prove_impl(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out) {
   if (!L || !sponge || !out) return ERR_INVALID;
   const auto t0 = std::chrono::steady_clock::now();
   auto trace_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
@@ -1427,8 +1485,11 @@ int lg_prove(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size
   }
   return s;
 }
+int lg_prove(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge, lg_proof** out) {
+  return lg::guard([&]() { return lg_prove_impl(L, var_idx, var_vals, n_vars, bump, sponge, out); });
+}
 
-int lg_prove_with_labels(lg_ligero* L, const char* const* labels, const uint64_t* var_vals, size_t n_vars, lg_sponge* sponge,
+static int lg_prove_with_labels_impl(lg_ligero* L, const char* const* labels, const uint64_t* var_vals, size_t n_vars, lg_sponge* sponge,
                          lg_proof** out) {
   if (!L || (!labels && n_vars)) return ERR_INVALID;
   std::vector<size_t> idx(n_vars);
@@ -1439,8 +1500,12 @@ int lg_prove_with_labels(lg_ligero* L, const char* const* labels, const uint64_t
   }
   return lg_prove(L, idx.data(), var_vals, n_vars, 0, sponge, out);
 }
+int lg_prove_with_labels(lg_ligero* L, const char* const* labels, const uint64_t* var_vals, size_t n_vars, lg_sponge* sponge,
+                         lg_proof** out) {
+  return lg::guard([&]() { return lg_prove_with_labels_impl(L, labels, var_vals, n_vars, sponge, out); });
+}
 
-int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted) {
+static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted) {
   if (!L || !P || !sponge || !accepted) return ERR_INVALID;
   *accepted = 0;
   lg_ctx* ctx = L->ctx;
@@ -1594,6 +1659,9 @@ int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted)
   *accepted = 1;
   return OK;
 }
+int lg_verify(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, int* accepted) {
+  return lg::guard([&]() { return lg_verify_impl(L, P, sponge, accepted); });
+}
 
 // ---------------------------------------------------------------------------------------------------
 // proof container
@@ -1604,7 +1672,7 @@ int lg_ligero_constraints(const lg_ligero* L, const lg_constraints** out) {
   return OK;
 }
 
-int lg_proof_assemble(const uint8_t root[32], const uint64_t* preenc_u_lc, size_t k, const uint64_t* linear_poly,
+static int lg_proof_assemble_impl(const uint8_t root[32], const uint64_t* preenc_u_lc, size_t k, const uint64_t* linear_poly,
                       size_t linear_len, const uint64_t* quadratic_poly, size_t quadratic_len, size_t t, size_t rows,
                       size_t depth, const uint64_t* const cols[3], const uint64_t* const idx[3],
                       const uint8_t* const sib[3], const uint8_t* const auth[3], lg_proof** out) {
@@ -1641,12 +1709,18 @@ int lg_proof_assemble(const uint8_t root[32], const uint64_t* preenc_u_lc, size_
   *out = P;
   return OK;
 }
+int lg_proof_assemble(const uint8_t root[32], const uint64_t* preenc_u_lc, size_t k, const uint64_t* linear_poly,
+                      size_t linear_len, const uint64_t* quadratic_poly, size_t quadratic_len, size_t t, size_t rows,
+                      size_t depth, const uint64_t* const cols[3], const uint64_t* const idx[3],
+                      const uint8_t* const sib[3], const uint8_t* const auth[3], lg_proof** out) {
+  return lg::guard([&]() { return lg_proof_assemble_impl(root, preenc_u_lc, k, linear_poly, linear_len, quadratic_poly, quadratic_len, t, rows, depth, cols, idx, sib, auth, out); });
+}
 
 int lg_proof_free(lg_proof* p) {
   delete p;
   return OK;
 }
-int lg_proof_serialize(const lg_proof* P, uint8_t* buf, size_t cap, size_t* len_out) {
+static int lg_proof_serialize_impl(const lg_proof* P, uint8_t* buf, size_t cap, size_t* len_out) {
   if (!P || !len_out) return ERR_INVALID;
   Writer w(buf, cap);
   w.digest(P->root);
@@ -1659,7 +1733,10 @@ int lg_proof_serialize(const lg_proof* P, uint8_t* buf, size_t cap, size_t* len_
   *len_out = w.pos;
   return w.ok ? OK : ERR_INVALID;  // buffer too small
 }
-int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out) {
+int lg_proof_serialize(const lg_proof* P, uint8_t* buf, size_t cap, size_t* len_out) {
+  return lg::guard([&]() { return lg_proof_serialize_impl(P, buf, cap, len_out); });
+}
+static int lg_proof_deserialize_impl(const uint8_t* buf, size_t len, lg_proof** out) {
   if (!buf || !out) return ERR_INVALID;
   Reader rd{buf, len};
   lg_proof* P = new (std::nothrow) lg_proof();
@@ -1677,6 +1754,9 @@ int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out) {
   }
   *out = P;
   return OK;
+}
+int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out) {
+  return lg::guard([&]() { return lg_proof_deserialize_impl(buf, len, out); });
 }
 
 }  // extern "C"

@@ -89,11 +89,14 @@ int lg_expand_fr(lg_ctx* ctx, const uint8_t seed[32], size_t count, uint64_t* ou
   return OK;
 }
 
-int lg_expand_indices(const uint8_t seed[32], size_t n, size_t t, uint64_t* idx_out) {
+static int lg_expand_indices_impl(const uint8_t seed[32], size_t n, size_t t, uint64_t* idx_out) {
   if (!seed || !idx_out || n == 0 || t > n) return ERR_INVALID;
   const std::vector<uint64_t> v = distinct_indices(seed, n, t);
   memcpy(idx_out, v.data(), v.size() * sizeof(uint64_t));
   return OK;
+}
+int lg_expand_indices(const uint8_t seed[32], size_t n, size_t t, uint64_t* idx_out) {
+  return lg::guard([&]() { return lg_expand_indices_impl(seed, n, t, idx_out); });
 }
 
 int lg_row_combine(lg_matrix* h, const uint64_t* r, uint64_t* out) {
@@ -113,7 +116,7 @@ int lg_row_combine(lg_matrix* h, const uint64_t* r, uint64_t* out) {
   return OK;
 }
 
-int lg_constraints_create(lg_ctx* ctx, size_t mk, const uint32_t* col_ptr, const uint32_t* row_idx, const uint32_t* val_id,
+static int lg_constraints_create_impl(lg_ctx* ctx, size_t mk, const uint32_t* col_ptr, const uint32_t* row_idx, const uint32_t* val_id,
                           size_t nnz, const uint64_t* const_table, size_t n_consts, lg_constraints** out) {
   if (!ctx || !out || !col_ptr || mk == 0 || (nnz && (!row_idx || !val_id)) || (n_consts && !const_table)) return ERR_INVALID;
   Ctx* c = &ctx->c;
@@ -146,6 +149,10 @@ int lg_constraints_create(lg_ctx* ctx, size_t mk, const uint32_t* col_ptr, const
   }
   *out = a;
   return OK;
+}
+int lg_constraints_create(lg_ctx* ctx, size_t mk, const uint32_t* col_ptr, const uint32_t* row_idx, const uint32_t* val_id,
+                          size_t nnz, const uint64_t* const_table, size_t n_consts, lg_constraints** out) {
+  return lg::guard([&]() { return lg_constraints_create_impl(ctx, mk, col_ptr, row_idx, val_id, nnz, const_table, n_consts, out); });
 }
 
 int lg_constraints_free(lg_constraints* a) {
@@ -224,7 +231,7 @@ static int linear_test_core(lg_matrix* h, Fr* r_a, uint64_t* coeffs_out, size_t*
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);
 }
 
-int lg_linear_test(lg_matrix* h, const lg_constraints* a, const uint64_t* r_linear, uint64_t* coeffs_out, size_t* len_out) {
+static int lg_linear_test_impl(lg_matrix* h, const lg_constraints* a, const uint64_t* r_linear, uint64_t* coeffs_out, size_t* len_out) {
   if (!h || !a || !r_linear) return ERR_INVALID;
   Matrix& m = h->m;
   Ctx* c = m.ctx;
@@ -237,8 +244,11 @@ int lg_linear_test(lg_matrix* h, const lg_constraints* a, const uint64_t* r_line
   LG_TRY(compute_r_a_inplace(c, a, (Fr*)ra.p));
   return linear_test_core(h, (Fr*)ra.p, coeffs_out, len_out);
 }
+int lg_linear_test(lg_matrix* h, const lg_constraints* a, const uint64_t* r_linear, uint64_t* coeffs_out, size_t* len_out) {
+  return lg::guard([&]() { return lg_linear_test_impl(h, a, r_linear, coeffs_out, len_out); });
+}
 
-int lg_linear_test_seeded(lg_matrix* h, const lg_constraints* a, const uint8_t seed[32], uint64_t* coeffs_out, size_t* len_out) {
+static int lg_linear_test_seeded_impl(lg_matrix* h, const lg_constraints* a, const uint8_t seed[32], uint64_t* coeffs_out, size_t* len_out) {
   if (!h || !a || !seed) return ERR_INVALID;
   Matrix& m = h->m;
   Ctx* c = m.ctx;
@@ -251,8 +261,11 @@ int lg_linear_test_seeded(lg_matrix* h, const lg_constraints* a, const uint8_t s
   LG_TRY(compute_r_a_inplace(c, a, (Fr*)ra.p));
   return linear_test_core(h, (Fr*)ra.p, coeffs_out, len_out);
 }
+int lg_linear_test_seeded(lg_matrix* h, const lg_constraints* a, const uint8_t seed[32], uint64_t* coeffs_out, size_t* len_out) {
+  return lg::guard([&]() { return lg_linear_test_seeded_impl(h, a, seed, coeffs_out, len_out); });
+}
 
-int lg_quadratic_test(lg_matrix* h, const uint64_t* r_quad, uint64_t* coeffs_out, size_t* len_out) {
+static int lg_quadratic_test_impl(lg_matrix* h, const uint64_t* r_quad, uint64_t* coeffs_out, size_t* len_out) {
   if (!h || !r_quad) return ERR_INVALID;
   Matrix& m = h->m;
   Ctx* c = m.ctx;
@@ -266,6 +279,9 @@ int lg_quadratic_test(lg_matrix* h, const uint64_t* r_quad, uint64_t* coeffs_out
   LG_TRY(qhat.alloc(c, 2 * m.k * sizeof(Fr)));
   LG_TRY(quadratic_evals_dev(m, (const Fr*)rin.ptr, (Fr*)qhat.p));
   return finish_poly(c, (Fr*)qhat.p, m.log_k, coeffs_out, len_out);
+}
+int lg_quadratic_test(lg_matrix* h, const uint64_t* r_quad, uint64_t* coeffs_out, size_t* len_out) {
+  return lg::guard([&]() { return lg_quadratic_test_impl(h, r_quad, coeffs_out, len_out); });
 }
 
 // ---- the same tests in pieces, for a column-sharded matrix (one rank's columns) -----------
@@ -310,7 +326,7 @@ int lg_quadratic_evals(lg_matrix* h, const uint64_t* r_quad, uint64_t* evals_out
   return OK;
 }
 
-int lg_poly_from_evals(lg_ctx* ctx, const uint64_t* evals, size_t size, uint64_t* coeffs_out, size_t* len_out) {
+static int lg_poly_from_evals_impl(lg_ctx* ctx, const uint64_t* evals, size_t size, uint64_t* coeffs_out, size_t* len_out) {
   if (!ctx || !evals || size < 4 || (size & (size - 1))) return ERR_INVALID;
   Ctx* c = &ctx->c;
   cudaSetDevice(c->device);
@@ -320,6 +336,9 @@ int lg_poly_from_evals(lg_ctx* ctx, const uint64_t* evals, size_t size, uint64_t
   LG_TRY(q.alloc(c, size * sizeof(Fr)));
   LG_CUDA(c, cudaMemcpyAsync(q.p, evals, size * sizeof(Fr), cudaMemcpyDefault, c->stream));
   return finish_poly(c, (Fr*)q.p, log_k, coeffs_out, len_out);
+}
+int lg_poly_from_evals(lg_ctx* ctx, const uint64_t* evals, size_t size, uint64_t* coeffs_out, size_t* len_out) {
+  return lg::guard([&]() { return lg_poly_from_evals_impl(ctx, evals, size, coeffs_out, len_out); });
 }
 
 int lg_open(lg_matrix* h, const uint64_t* idx, size_t t, uint64_t* cols_out, uint8_t* sib_out, uint8_t* auth_out) {

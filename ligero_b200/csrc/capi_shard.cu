@@ -258,10 +258,15 @@ int encode_runs(lg_shard* s, const uint64_t* local, uint32_t rho, void* const* d
   Ctx* c = &s->ctx->c;
   if (s->log_k > 10) LG_TRY(ensure_scratch(s, (size_t)(rho - 1) * s->max_run * s->k * sizeof(Fr)));
   const int groups_saved = c->persist_groups;
+  static int overlap_groups = -1;  // LG_SHARD_GROUPS=3 keeps the three-group encoder while a hash kernel shares the SMs
+  if (overlap_groups < 0) {
+    const char* e = getenv("LG_SHARD_GROUPS");
+    overlap_groups = (e && atoi(e) == 3) ? 3 : 2;
+  }
   for (size_t j = 0; j < s->runs.size(); j++) {
     const Run& r = s->runs[j];
     // while a hash kernel shares the SMs the encoder runs two groups per SM and leaves it a third of the registers
-    if (hash && s->world > 1 && groups_saved == 3) c->persist_groups = (j == 0) ? 3 : 2;
+    if (hash && s->world > 1 && groups_saved == 3) c->persist_groups = (j == 0) ? 3 : overlap_groups;
     int st = OK;
     if (r.nrows)
       st = lg_encode_sharded_rows(s->ctx, local + r.local_off * s->k * 4, r.nrows, r.row_base, s->rows, s->k, rho, dst, s->world,
@@ -485,7 +490,7 @@ static int on_all(lg_mgpu* g, F fn) {
 
 extern "C" {
 
-int lg_shard_create(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_inv, int rank, int world, size_t t_max, int sub_blocks,
+static int lg_shard_create_impl(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_inv, int rank, int world, size_t t_max, int sub_blocks,
                     lg_shard** out) {
   if (!ctx || !out) return ERR_INVALID;
   Ctx* c = &ctx->c;
@@ -548,6 +553,10 @@ int lg_shard_create(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_inv, int rank,
   }
   *out = s;
   return OK;
+}
+int lg_shard_create(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_inv, int rank, int world, size_t t_max, int sub_blocks,
+                    lg_shard** out) {
+  return lg::guard([&]() { return lg_shard_create_impl(ctx, m, k, rho_inv, rank, world, t_max, sub_blocks, out); });
 }
 
 int lg_shard_free(lg_shard* s) {
@@ -692,7 +701,7 @@ int lg_shard_commit(lg_shard* s, const uint64_t* msg_local, uint8_t root_out[32]
 
 // the commit-and-test transcript (src/ligero/mod.rs:457-578) on this rank's rows of a ready pre-encoding matrix;
 // every rank runs the same Fiat-Shamir transcript on the gathered values.  out may be NULL (this rank only helps).
-int lg_shard_prove_matrix(lg_shard* s, lg_ligero* L, const uint64_t* local_rows, lg_sponge* sponge, lg_proof** out) {
+static int lg_shard_prove_matrix_impl(lg_shard* s, lg_ligero* L, const uint64_t* local_rows, lg_sponge* sponge, lg_proof** out) {
   if (!s || !L || !sponge) return ERR_INVALID;
   Ctx* c = &s->ctx->c;
   cudaSetDevice(c->device);
@@ -771,10 +780,13 @@ int lg_shard_prove_matrix(lg_shard* s, lg_ligero* L, const uint64_t* local_rows,
   return lg_proof_assemble(root, (const uint64_t*)lc.data(), k, (const uint64_t*)lin.data(), lin_len, (const uint64_t*)quad.data(), quad_len,
                            t, rows, (size_t)log_n - 1, cols3, idx3, sib3, auth3, out);
 }
+int lg_shard_prove_matrix(lg_shard* s, lg_ligero* L, const uint64_t* local_rows, lg_sponge* sponge, lg_proof** out) {
+  return lg::guard([&]() { return lg_shard_prove_matrix_impl(s, L, local_rows, sponge, out); });
+}
 
 // LigeroCircuit::prove over the shards from the variable assignment: every rank runs the (cheap, replicated) evaluation
 // trace on its own GPU, keeps its rows of [X;Y;Z;W] and goes on with lg_shard_prove_matrix
-int lg_shard_prove(lg_shard* s, lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge,
+static int lg_shard_prove_impl(lg_shard* s, lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge,
                    lg_proof** out) {
   if (!s || !L || !sponge) return ERR_INVALID;
   Ctx* c = &s->ctx->c;
@@ -788,6 +800,10 @@ int lg_shard_prove(lg_shard* s, lg_ligero* L, const size_t* var_idx, const uint6
     LG_CUDA(c, cudaGetLastError());
   }
   return lg_shard_prove_matrix(s, L, (const uint64_t*)s->pre_local, sponge, out);
+}
+int lg_shard_prove(lg_shard* s, lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge,
+                   lg_proof** out) {
+  return lg::guard([&]() { return lg_shard_prove_impl(s, L, var_idx, var_vals, n_vars, bump, sponge, out); });
 }
 
 int lg_shard_last_ms(const lg_shard* s, double ms_out[4]) {
@@ -827,7 +843,7 @@ const char* lg_mgpu_last_error(const lg_mgpu* g) { return g ? g->error.c_str() :
 lg_ctx* lg_mgpu_ctx(lg_mgpu* g, int i) { return (g && i >= 0 && i < g->world) ? g->ctx[i] : nullptr; }
 
 // encode + commit of a whole rows x k host (or device-0 ... any addressable) matrix over all GPUs: root only
-int lg_mgpu_commit(lg_mgpu* g, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, uint8_t root_out[32]) {
+static int lg_mgpu_commit_impl(lg_mgpu* g, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, uint8_t root_out[32]) {
   if (!g || !preenc_u || rows % 4) return ERR_INVALID;
   lg_shard* sh[kMaxRanks] = {};
   int st = on_all(g, [&](int i) { return lg_shard_create(g->ctx[i], rows / 4, k, rho_inv, i, g->world, 0, 1, &sh[i]); });
@@ -848,8 +864,11 @@ int lg_mgpu_commit(lg_mgpu* g, const uint64_t* preenc_u, size_t rows, size_t k, 
     if (sh[i]) lg_shard_free(sh[i]);
   return st;
 }
+int lg_mgpu_commit(lg_mgpu* g, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, uint8_t root_out[32]) {
+  return lg::guard([&]() { return lg_mgpu_commit_impl(g, preenc_u, rows, k, rho_inv, root_out); });
+}
 
-int lg_mgpu_ligero_new(lg_mgpu* g, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_mligero** out) {
+static int lg_mgpu_ligero_new_impl(lg_mgpu* g, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_mligero** out) {
   if (!g || !circuit || !out) return ERR_INVALID;
   lg_mligero* ml = new (std::nothrow) lg_mligero();
   if (!ml) return ERR_NOMEM;
@@ -869,6 +888,9 @@ int lg_mgpu_ligero_new(lg_mgpu* g, const lg_circuit* circuit, const size_t* outp
   *out = ml;
   return OK;
 }
+int lg_mgpu_ligero_new(lg_mgpu* g, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_mligero** out) {
+  return lg::guard([&]() { return lg_mgpu_ligero_new_impl(g, circuit, outputs, n_outputs, lambda, out); });
+}
 
 int lg_mgpu_ligero_free(lg_mligero* ml) {
   if (!ml) return OK;
@@ -881,7 +903,7 @@ int lg_mgpu_ligero_free(lg_mligero* ml) {
 }
 
 // LigeroCircuit::prove (bump != 0) / prove_inner over all GPUs; the caller's sponge is advanced exactly as by lg_prove
-int lg_mgpu_prove(lg_mligero* ml, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge,
+static int lg_mgpu_prove_impl(lg_mligero* ml, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge,
                   lg_proof** out) {
   if (!ml || !sponge || !out) return ERR_INVALID;
   lg_mgpu* g = ml->mg;
@@ -891,6 +913,10 @@ int lg_mgpu_prove(lg_mligero* ml, const size_t* var_idx, const uint64_t* var_val
   int st = on_all(g, [&](int i) { return lg_shard_prove(ml->sh[i], ml->L[i], var_idx, var_vals, n_vars, bump, sp[i], i == 0 ? out : nullptr); });
   for (int i = 1; i < g->world; i++) lg_sponge_free(sp[i]);
   return st;
+}
+int lg_mgpu_prove(lg_mligero* ml, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, lg_sponge* sponge,
+                  lg_proof** out) {
+  return lg::guard([&]() { return lg_mgpu_prove_impl(ml, var_idx, var_vals, n_vars, bump, sponge, out); });
 }
 
 }  // extern "C"

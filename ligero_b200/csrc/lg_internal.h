@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <map>
+#include <new>
+#include <stdexcept>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -25,6 +27,17 @@ enum Status : int {
 
 struct Ctx;
 int set_error(Ctx* ctx, int code, const std::string& msg);
+// nothing unwinds across the C ABI: allocation failures of the host containers become LG_ERR_NOMEM
+template <class F>
+inline int guard(F&& body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return ERR_NOMEM;
+  } catch (const std::exception&) {
+    return ERR_STATE;
+  }
+}
 #define LG_CUDA(ctx, expr)                                                                         \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \

@@ -1,51 +1,13 @@
 """torchrun --nproc-per-node G scripts/mgpu_prove_check.py [log2_gates ...]
 
-Multi-GPU prover (ligero_b200.parallel.ShardedProver) == single-GPU prover, byte for byte, on seeded random
-Add/Mul circuits; the sharded proof is also put through LigeroCircuit::verify.  (The single-GPU prover is pinned to
-the oracle by tests/test_gpu_host_driver.py.)"""
-import os, random, sys, time
+Multi-GPU prover (lg_shard_prove*, through ligero_b200.parallel.ShardedProver) == single-GPU prover, byte for byte, on
+the seeded synthetic Add/Mul circuits (lg_circuit_synthetic); the sharded proof is also put through LigeroCircuit::verify.
+(The single-GPU prover is pinned to the oracle by tests/test_gpu_host_driver.py.)  Prints MGPU_PROVE_OK / _FAIL."""
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 import ligero_b200 as lb
 from ligero_b200 import parallel as par
-
-P = 21888242871839275222246405745257275088548364400416034343698204186575808495617
-
-
-def random_circuit(gates: int, seed: int):
-    """seeded Add/Mul circuit of about `gates` gates and depth O(log gates); every node is reachable from the single
-    Add output, whose value is 1; no gate has two constant operands"""
-    rnd = random.Random(seed)
-    c = lb.ArithmeticCircuit()
-    one = c.constant(1)
-    x, y = c.new_variable(), c.new_variable()
-    vals = {one: 1, x: rnd.randrange(P), y: rnd.randrange(P)}
-    nodes, unused = [x, y], {x, y}
-    for _ in range(gates // 2):
-        a, b = rnd.choice(nodes), rnd.choice(nodes)
-        if rnd.random() < 0.5:
-            node, v = c.mul(a, b), vals[a] * vals[b] % P
-        else:
-            node, v = c.add(a, b), (vals[a] + vals[b]) % P
-        vals[node] = v
-        unused.discard(a)
-        unused.discard(b)
-        unused.add(node)
-        nodes.append(node)
-    level = sorted(unused)
-    while len(level) > 1:                      # balanced sum of everything not yet consumed
-        nxt = []
-        for i in range(0, len(level) - 1, 2):
-            n2 = c.add(level[i], level[i + 1])
-            vals[n2] = (vals[level[i]] + vals[level[i + 1]]) % P
-            nxt.append(n2)
-        if len(level) & 1:
-            nxt.append(level[-1])
-        level = nxt
-    k = c.constant((1 - vals[level[0]]) % P)
-    out = c.add(level[0], k)
-    return c, out, [(x, vals[x]), (y, vals[y])]
-
 
 def main():
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -54,7 +16,7 @@ def main():
     ctx = lb.Context(lr)
     ok = True
     for lg in [int(a) for a in sys.argv[1:]] or [6, 10, 14]:
-        circ, out, assignment = random_circuit(1 << lg, 100 + lg)
+        circ, out, assignment = lb.ArithmeticCircuit.synthetic(1 << lg, 100 + lg)
         L = lb.LigeroCircuit(ctx, circ, [out], lb.DEFAULT_SECURITY_LEVEL)
         if L.k % world or (L.n // world) < 2:
             if rank == 0:

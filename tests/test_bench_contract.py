@@ -18,9 +18,27 @@ def test_shapes_of_the_synthetic_configurations():
 
 def test_committed_ncu_summary_feeds_the_roofline_traffic():
     import bench
-    t = bench.ncu_traffic("ntt_local_kernel", 16388, 8192)
+    t = bench.ncu_traffic("ntt_persist_kernel", 16388, 8192)
     assert t is not None and 30e9 < t < 45e9          # algorithmic 34.4 GB per launch
-    assert bench.ncu_traffic("ntt_local_kernel", 4100, 2048) is None
+    assert bench.ncu_traffic("ntt_persist_kernel", 4100, 2048) is None
+    # captures of kernels the loaded library does not contain, or of earlier rounds, are refused
+    assert bench.ncu_traffic("no_such_kernel", 16388, 8192) is None
+    assert bench.ncu_traffic("ntt_local_kernel", 16388, 8192) is None      # only round-1 captures exist for it
+
+
+def test_micro_workload_shapes_and_work_counts():
+    import argparse
+    import bench
+    ns = argparse.Namespace(workload="micro", rows=1 << 14, n=1 << 16, rho_inv=0, log_gates=24)
+    assert bench.resolve_shape(ns) == (16384, 16384, 65536, 4096, 4, None)
+    ns = argparse.Namespace(workload="circuit", rows=0, n=0, rho_inv=0, log_gates=20)
+    assert bench.resolve_shape(ns) == (4100, 2048, 16384, 1025, 8, 20)
+    # executed products never exceed the algorithmic count by more than the unit twiddles the persistent kernel keeps
+    for (R, k, rho) in [(16388, 8192, 8), (4100, 2048, 8), (16384, 16384, 4), (344, 128, 8)]:
+        q = k.bit_length() - 1
+        w_mul = R * ((k // 2) * q + (rho - 1) * ((k // 2) * q + k))
+        assert 0.85 * w_mul <= bench.executed_products(R, k, rho) <= w_mul
+    assert bench.pinned_root(24) == "73f425e9a839a6eb3b624ce34e2ca26e3e9b36681e8c71ad307ebbd349cdc55c"
 
 
 def test_reference_arm_prints_the_contract_line():

@@ -75,3 +75,25 @@ def test_malformed_images_are_refused():
     # a wire id beyond nWires
     with pytest.raises(LigeroB200Error):
         ArithmeticCircuit.from_r1cs_bytes(write_r1cs([[(1, nw + 3)]], [[(1, 1)]], [[(1, 2)]], nw))
+
+
+def test_header_counts_must_be_justified_by_the_file():
+    """a crafted nWires (or nConstraints) that the file cannot back must be refused before it drives an
+    allocation (the header field is a u32; 0xF0000000 labelled variables would exhaust memory)."""
+    a, b, c, nw, _ = load_r1cs("multiplication")
+    good = bytearray(write_r1cs(a, b, c, nw))
+    hdr = bytes(good).index(struct.pack("<I", 32) + P.to_bytes(32, "little"))      # start of the header payload
+    for field_off, value in ((4 + 32, 0xF0000000), (4 + 32, nw + 1), (4 + 32 + 16 + 8, 0xF0000000)):
+        bad = bytearray(good)
+        bad[hdr + field_off: hdr + field_off + 4] = struct.pack("<I", value)
+        with pytest.raises(LigeroB200Error):
+            ArithmeticCircuit.from_r1cs_bytes(bytes(bad))
+    # the reference's own fixture (no tampering) still loads when present in this container
+    ref = "/root/reference/circom/multiplication.r1cs"
+    if os.path.exists(ref):
+        data = bytearray(open(ref, "rb").read())
+        ArithmeticCircuit.from_r1cs_bytes(bytes(data))
+        pos = bytes(data).index(P.to_bytes(32, "little")) + 32
+        data[pos: pos + 4] = struct.pack("<I", 0xF0000000)
+        with pytest.raises(LigeroB200Error):
+            ArithmeticCircuit.from_r1cs_bytes(bytes(data))
