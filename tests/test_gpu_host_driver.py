@@ -207,3 +207,24 @@ def test_repeated_squaring_10_proof_equals_oracle(gpu_ctx):
     bad = list(va)
     bad[0] = (1, (wit[1] + 1) % P)
     assert not lc.verify(lc.prove(bad, lb.PoseidonSponge.test_sponge()), lb.PoseidonSponge.test_sponge())
+
+
+def test_rust_parity_dump_when_present(gpu_ctx):
+    """GPU prover against the REAL reference: when rust/ligero-parity-dump/run.sh has produced
+    tests/golden/rust_parity_dump.json, the serialized GPU proofs of lemniscate / determinant / poseidon must be the
+    reference's bytes (src/ligero/tests.rs:197-243, 365-415 with DETERMINISTIC_TEST_RNG=1).  Skipped without the file."""
+    import json
+    from tests.test_golden import rust_dump_path
+    path = rust_dump_path()
+    if path is None:
+        pytest.skip("no reference-produced dump: parity unpinned (see rust/ligero-parity-dump/run.sh)")
+    dump = json.load(open(path))
+    for name in ("lemniscate", "determinant"):
+        oc, _, assign = CASES[name]()
+        lc = lb.LigeroCircuit(gpu_ctx, mirror_circuit(oc), [oc.last()])
+        assert lc.prove(assign, lb.PoseidonSponge.test_sponge()).to_bytes().hex() == dump[name]["proof_hex"], name
+    a, b, c, nw, wit = load_r1cs("poseidon")
+    circ, outs = lb.ArithmeticCircuit.from_constraint_system(a, b, c, nw)
+    lc = lb.LigeroCircuit(gpu_ctx, circ, outs)
+    blob = lc.prove(list(enumerate(wit))[1:], lb.PoseidonSponge.test_sponge()).to_bytes()
+    assert blob.hex() == dump["poseidon"]["proof_hex"], "poseidon"
