@@ -330,7 +330,9 @@ int lg_shard_handles(lg_shard* s, uint8_t out[192]);
 int lg_shard_connect(lg_shard* s, const uint8_t* all_handles);
 /* the same for shards that live in ONE process (enables peer access between their devices) */
 int lg_shard_connect_local(lg_shard* const* shards, int world);
-/* hash the row blocks that have arrived behind the encoding of the next (default on; LG_SHARD_PIPELINE=0) */
+/* hash the row blocks that have arrived behind the encoding of the next: 1 on, 0 off, -1 (default) by world size
+ * (on from 4 GPUs, where a rank's column hash is a latency chain; LG_SHARD_PIPELINE=0/1 in the environment overrides).
+ * Every rank of a group must use the same setting. */
 int lg_shard_set_pipeline(lg_shard* s, int enabled);
 /* This rank's rows: 4*sub_blocks runs of consecutive global rows, in the order its local matrix stores them
  * (with sub_blocks = 1: [X_g; Y_g; Z_g; W_g]).  row_base / nrows: capacity 4*sub_blocks each, nullable. */

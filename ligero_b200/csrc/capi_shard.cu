@@ -161,7 +161,7 @@ struct lg_shard {
   int log_k = 0, log_n_local = 0;
   size_t t_max = 0;
   int sub = 1;                 // sub-blocks per X/Y/Z/W block: the commit pipeline has 4*sub steps
-  bool pipeline = true;
+  int pipeline = -1;           // 1 / 0: block pipeline on / off; -1: by world size (measured: on from 4 GPUs)
   std::vector<ShardRun> runs;
   size_t rows_local = 0, max_run = 0;
   lg_matrix* cols = nullptr;   // this rank's column shard of U (rows x kg, rho planes)
@@ -293,7 +293,12 @@ int commit_async(lg_shard* s, const uint64_t* local) {
   if (!s->connected) return sfail(s, ERR_STATE, "lg_shard_connect first");
   if (!local && s->rows_local) return sfail(s, ERR_INVALID, "null input matrix");
   Matrix& m = s->cols->m;
-  if (s->pipeline) {
+  // Measured on B200 (2^24-gate shape): with 2 GPUs a rank owns 32 768 columns, its hash saturates the ALU pipe and
+  // sharing the SMs with it costs the encoder more than the overlap saves (77 vs 67 ms per step); from 4 GPUs on the
+  // hash is a latency chain over few columns and runs behind the encoder.  Host input is the exception: the upload
+  // makes the encoder wait anyway (lg_shard_set_pipeline(1) there: 79 vs 89 ms end to end at 2 GPUs).
+  const bool pipe = s->pipeline < 0 ? s->world >= 4 : s->pipeline != 0;
+  if (pipe) {
     LG_TRY(hash_pipeline_setup(c, m.n));
     // the hash stream must not start on a new commitment before the previous one's consumers are done
     LG_CUDA(c, cudaEventRecord(s->ev_step, c->stream));
@@ -517,7 +522,7 @@ static int lg_shard_create_impl(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_in
   while (((size_t)1 << s->log_n_local) < s->n_local) s->log_n_local++;
   s->t_max = t_max;
   s->sub = sub_blocks;
-  if (const char* e = getenv("LG_SHARD_PIPELINE")) s->pipeline = atoi(e) != 0;
+  if (const char* e = getenv("LG_SHARD_PIPELINE")) s->pipeline = atoi(e) != 0 ? 1 : 0;
   build_runs(s);
   int st = lg_matrix_create(ctx, s->rows, s->kg, rho_inv, &s->cols);
   if (st == OK && t_max) st = lg_matrix_create(ctx, s->rows, s->kg, 2, &s->rhat);
@@ -661,7 +666,7 @@ int lg_shard_connect_local(lg_shard* const* shards, int world) {
 
 int lg_shard_set_pipeline(lg_shard* s, int enabled) {
   if (!s) return ERR_INVALID;
-  s->pipeline = enabled != 0;
+  s->pipeline = enabled < 0 ? -1 : (enabled != 0 ? 1 : 0);
   return OK;
 }
 

@@ -7,6 +7,7 @@
 #include <new>
 #include <stdexcept>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -71,6 +72,8 @@ struct Ctx {
   int sm_count = 148;
   std::string last_error;
   std::map<std::pair<int, int>, NttTables> tables;  // (log_k, rho_inv | plain << 16)
+  // kernels whose dynamic shared-memory limit has been raised on THIS device (the attribute is per device)
+  std::set<const void*> smem_configured;
   // kernel launch counter (bench.py's "gpu_launches")
   uint64_t launches = 0;
   // scratch reused across calls

@@ -677,11 +677,12 @@ template <int MAXR, int MINB, int MODE, int NT = (1 << (kLogE - MAXR))>
 static int launch_local_v(Ctx* ctx, const LocalArgs& a) {
   constexpr int E = 1 << kLogE;
   const size_t smem = 4 * E * sizeof(uint4);
-  static bool configured = false;
-  if (!configured) {
+  // (per device, not per process: one process may drive several GPUs -- lg_mgpu_*)
+  const void* fn = (const void*)ntt_local_kernel<kLogE, MAXR, MINB, MODE, NT>;
+  if (!ctx->smem_configured.count(fn)) {
     LG_CUDA(ctx, cudaFuncSetAttribute(ntt_local_kernel<kLogE, MAXR, MINB, MODE, NT>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    ctx->smem_configured.insert(fn);
   }
   const unsigned long long ctas = (a.total + E - 1) / E;
   ntt_local_kernel<kLogE, MAXR, MINB, MODE, NT><<<(unsigned)ctas, NT, smem, ctx->stream>>>(a);
@@ -718,10 +719,10 @@ static int launch_local(Ctx* ctx, const LocalArgs& a) {
 template <int GROUPS, bool CAPPED>
 static int launch_persist_g(Ctx* ctx, const LocalArgs& a) {
   const size_t smem = kPersistTwBytes + GROUPS * kPersistGroupBytes;
-  static bool configured = false;
-  if (!configured) {
+  const void* fn = (const void*)ntt_persist_kernel<GROUPS, CAPPED>;
+  if (!ctx->smem_configured.count(fn)) {  // per device: one process may drive several GPUs
     LG_CUDA(ctx, cudaFuncSetAttribute(ntt_persist_kernel<GROUPS, CAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    ctx->smem_configured.insert(fn);
   }
   const unsigned long long chunks = a.total >> kLogPE;
   unsigned long long ctas = (chunks + GROUPS - 1) / GROUPS;

@@ -172,14 +172,20 @@ class ShardedCommitter:
         self.row_ids = local_row_ids(m, world, rank, sub_blocks)
         self.rows_g, self.kg = len(self.row_ids), k // world
         self.handle = _make_shard(ctx, m, k, rho, rank, world, t_max, sub_blocks)
-        if pipeline is not None:
-            check(ctx.lib.lg_shard_set_pipeline(self.handle, int(bool(pipeline))), ctx.handle, "lg_shard_set_pipeline")
         self.pipeline = pipeline
+        if pipeline is not None:
+            self.set_pipeline(pipeline)
         self.dev = torch.device("cuda", ctx.device)
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=self.dev)
         self.mat_cols = CommittedMatrix(ctx, ctx.lib.lg_shard_matrix(self.handle), None)
         self.mat_cols.free = lambda: None            # borrowed: owned by the shard
         self.subtree_roots = None
+
+    def set_pipeline(self, enabled):
+        """True / False, or None for the library default (by world size).  Same setting on every rank."""
+        from .backend import check
+        v = -1 if enabled is None else int(bool(enabled))
+        check(self.ctx.lib.lg_shard_set_pipeline(self.handle, v), self.ctx.handle, "lg_shard_set_pipeline")
 
     def close(self):
         if getattr(self, "handle", None):
@@ -252,9 +258,17 @@ class ShardedCommitter:
         kernel_launches = {p: v[1] for p, v in phases.items() if v[1]}
         ctx.set_timing(False)
         value = R * k / (ms_per_step * 1e-3)
-        # end to end: pinned host shard -> device, root back on the host, every step
+        # end to end: pinned host shard -> device, root back on the host, every step (LG_BENCH_SKIP_E2E=1: tuning sweeps)
+        if os.environ.get("LG_BENCH_SKIP_E2E") == "1":
+            sc.close()
+            return {"metric": "fr_elems_per_s_encode_commit", "value": value, "unit": "Fr elems/s", "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                    "scaling": "strong", "config": {"rows": R, "k": k, "n": rho * k, "rho_inv": rho, "seed": seed},
+                    "e2e": None, "root": root0.hex(), "kernel_ms_rank0": kernel_ms, "gpu_launches": int(launches)}
         host = torch.empty_like(msg, device="cpu").pin_memory()
         host.copy_(msg)
+        if pipeline is None and "LG_SHARD_PIPELINE" not in os.environ:
+            sc.set_pipeline(True)        # host input: the upload paces the encoder, hashing behind it is free
         sc.commit(host)
         dist.barrier()
         torch.cuda.synchronize()
@@ -284,7 +298,8 @@ class ShardedCommitter:
             "root_check": ("equals the CPU-oracle root of the whole matrix (tests/golden/full_size_root.json)"
                            if expected_root is not None else "no pinned root for this shape"),
             "kernel_ms_rank0": kernel_ms, "kernel_launches_rank0": kernel_launches, "rows_per_rank": rows_g,
-            "hash_pipeline": os.environ.get("LG_SHARD_PIPELINE", "1") != "0" if pipeline is None else bool(pipeline),
+            "hash_pipeline": (bool(pipeline) if pipeline is not None else
+                              (os.environ["LG_SHARD_PIPELINE"] != "0" if "LG_SHARD_PIPELINE" in os.environ else world >= 4)),
         }
 
 

@@ -38,7 +38,8 @@ for lg in (10, 14):
         vals = fr_to_limbs([v for _, v in assign])
         for rep in range(2):
             h = c_void_p()
-            st = lib.lg_mgpu_prove(ml, _ptr(idx), _ptr(vals), len(idx), 1, lb.PoseidonSponge.test_sponge().handle, byref(h))
+            sponge = lb.PoseidonSponge.test_sponge()          # keep the object alive across the call
+            st = lib.lg_mgpu_prove(ml, _ptr(idx), _ptr(vals), len(idx), 1, sponge.handle, byref(h))
             same = st == 0 and lb.LigeroProof(h).to_bytes() == ref
             if not same:
                 break
