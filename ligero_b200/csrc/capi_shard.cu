@@ -161,7 +161,7 @@ struct lg_shard {
   int log_k = 0, log_n_local = 0;
   size_t t_max = 0;
   int sub = 1;                 // sub-blocks per X/Y/Z/W block: the commit pipeline has 4*sub steps
-  int pipeline = -1;           // 1 / 0: block pipeline on / off; -1: by world size (measured: on from 4 GPUs)
+  int pipeline = -1;           // block pipeline: 0 off, 1 eager, 2 deferred (see encode_runs); -1: by world size
   std::vector<ShardRun> runs;
   size_t rows_local = 0, max_run = 0;
   lg_matrix* cols = nullptr;   // this rank's column shard of U (rows x kg, rho planes)
@@ -175,7 +175,7 @@ struct lg_shard {
   unsigned long long epoch = 0;
   Fr* scratch = nullptr;       // coset intermediate of one run (k > 1024)
   size_t scratch_bytes = 0;
-  cudaEvent_t ev_step = nullptr, ev_done = nullptr;
+  cudaEvent_t ev_step = nullptr, ev_done = nullptr, ev_local[2] = {nullptr, nullptr};
   uint8_t* host_pin = nullptr; // pinned: header read-back (roots, err)
   uint32_t* local_src_rows = nullptr;  // device: global row of every local row (gather of r_a / the witness)
   Fr* pre_full = nullptr;      // 4mk, device trace output (lg_shard_prove)
@@ -224,9 +224,9 @@ int post(lg_shard* s, cudaStream_t st, size_t dst_off, const void* src_dev, size
   LG_CUDA(c, cudaGetLastError());
   return OK;
 }
-int wait_all(lg_shard* s, cudaStream_t st) {
+int wait_all(lg_shard* s, cudaStream_t st, unsigned long long epoch = 0) {
   Ctx* c = &s->ctx->c;
-  shard_wait_kernel<<<1, 32, 0, st>>>(s->mail, s->world, s->epoch, (long long)2e10);
+  shard_wait_kernel<<<1, 32, 0, st>>>(s->mail, s->world, epoch ? epoch : s->epoch, (long long)2e10);
   c->launches++;
   LG_CUDA(c, cudaGetLastError());
   return OK;
@@ -252,37 +252,55 @@ int ensure_scratch(lg_shard* s, size_t bytes) {
   return OK;
 }
 
-// encode every run of `local` (host or device, the rank's rows in run order) into the peers' shards `dst`;
-// hash != nullptr: the block pipeline (flag after every run, the owner hashes the block behind the next run)
-int encode_runs(lg_shard* s, const uint64_t* local, uint32_t rho, void* const* dst, bool plain, lg_matrix* hash) {
+// encode every run of `local` (host or device, the rank's rows in run order) into the peers' shards `dst`.
+// hash != nullptr: the block pipeline -- a flag after every run, and the owner hashes block j on its hash stream
+//   mode 1 (eager)   : as soon as block j has landed everywhere, i.e. beside the shared-memory kernel of run j+1, which
+//                      then runs two groups per SM and leaves the hash a third of the registers;
+//   mode 2 (deferred): when the shared-memory kernel of run j+1 is done, i.e. beside the last strided pass of run j+1,
+//                      whose warps mostly wait for their NVLink stores -- the encoder keeps all three groups.
+int encode_runs(lg_shard* s, const uint64_t* local, uint32_t rho, void* const* dst, bool plain, lg_matrix* hash, int mode) {
   Ctx* c = &s->ctx->c;
   if (s->log_k > 10) LG_TRY(ensure_scratch(s, (size_t)(rho - 1) * s->max_run * s->k * sizeof(Fr)));
   const int groups_saved = c->persist_groups;
-  static int overlap_groups = -1;  // LG_SHARD_GROUPS=3 keeps the three-group encoder while a hash kernel shares the SMs
+  static int overlap_groups = -1;  // LG_SHARD_GROUPS=3 keeps the three-group encoder in the eager mode too
   if (overlap_groups < 0) {
     const char* e = getenv("LG_SHARD_GROUPS");
     overlap_groups = (e && atoi(e) == 3) ? 3 : 2;
   }
+  auto hash_block = [&](const Run& r, unsigned long long epoch, cudaEvent_t after) -> int {
+    LG_CUDA(c, cudaStreamWaitEvent(c->hash_stream_hi, after, 0));
+    LG_TRY(wait_all(s, c->hash_stream_hi, epoch));
+    return hash_columns_range(c, c->hash_stream_hi, hash->m.u, hash->m.rows, hash->m.log_k, hash->m.rho_inv, r.blk0, r.blk1,
+                              c->hash_state, hash->m.leaves, s->ctx->col_len_prefix);
+  };
+  unsigned long long prev_epoch = 0;
   for (size_t j = 0; j < s->runs.size(); j++) {
     const Run& r = s->runs[j];
-    // while a hash kernel shares the SMs the encoder runs two groups per SM and leaves it a third of the registers
-    if (hash && s->world > 1 && groups_saved == 3) c->persist_groups = (j == 0) ? 3 : overlap_groups;
+    if (hash && mode == 1 && s->world > 1 && groups_saved == 3) c->persist_groups = (j == 0) ? 3 : overlap_groups;
+    cudaEvent_t ev_loc = s->ev_local[j & 1];
+    if (hash && mode == 2) c->ev_after_local = ev_loc;
     int st = OK;
     if (r.nrows)
       st = lg_encode_sharded_rows(s->ctx, local + r.local_off * s->k * 4, r.nrows, r.row_base, s->rows, s->k, rho, dst, s->world,
                                   (uint64_t*)s->scratch, plain ? 1 : 0);
+    else if (hash && mode == 2)
+      st = cudaEventRecord(ev_loc, c->stream) == cudaSuccess ? OK : ERR_CUDA;
     c->persist_groups = groups_saved;
+    c->ev_after_local = nullptr;
     LG_TRY(st);
     if (hash) {
       s->epoch++;
       shard_post_kernel<<<1, 32, 0, c->stream>>>(s->peers, s->world, s->rank, 0, nullptr, 0, s->epoch);
       c->launches++;
       LG_CUDA(c, cudaGetLastError());
-      LG_CUDA(c, cudaEventRecord(s->ev_step, c->stream));
-      LG_CUDA(c, cudaStreamWaitEvent(c->hash_stream_hi, s->ev_step, 0));
-      LG_TRY(wait_all(s, c->hash_stream_hi));
-      LG_TRY(hash_columns_range(c, c->hash_stream_hi, hash->m.u, hash->m.rows, hash->m.log_k, hash->m.rho_inv, r.blk0, r.blk1,
-                                c->hash_state, hash->m.leaves, s->ctx->col_len_prefix));
+      if (mode == 2) {
+        if (j > 0) LG_TRY(hash_block(s->runs[j - 1], prev_epoch, ev_loc));
+        prev_epoch = s->epoch;
+      }
+      if (mode == 1 || j + 1 == s->runs.size()) {
+        LG_CUDA(c, cudaEventRecord(s->ev_step, c->stream));
+        LG_TRY(hash_block(r, s->epoch, s->ev_step));
+      }
     }
   }
   return OK;
@@ -297,18 +315,18 @@ int commit_async(lg_shard* s, const uint64_t* local) {
   // sharing the SMs with it costs the encoder more than the overlap saves (77 vs 67 ms per step); from 4 GPUs on the
   // hash is a latency chain over few columns and runs behind the encoder.  Host input is the exception: the upload
   // makes the encoder wait anyway (lg_shard_set_pipeline(1) there: 79 vs 89 ms end to end at 2 GPUs).
-  const bool pipe = s->pipeline < 0 ? s->world >= 4 : s->pipeline != 0;
+  const int pipe = s->pipeline < 0 ? (s->world >= 4 ? 2 : 0) : s->pipeline;
   if (pipe) {
     LG_TRY(hash_pipeline_setup(c, m.n));
     // the hash stream must not start on a new commitment before the previous one's consumers are done
     LG_CUDA(c, cudaEventRecord(s->ev_step, c->stream));
     LG_CUDA(c, cudaStreamWaitEvent(c->hash_stream_hi, s->ev_step, 0));
-    LG_TRY(encode_runs(s, local, s->rho, s->peer_u, true, s->cols));
+    LG_TRY(encode_runs(s, local, s->rho, s->peer_u, true, s->cols, pipe));
     LG_TRY(merkle_build(c, m.leaves, m.n, m.nodes, s->ctx->leaf_len_prefix, c->hash_stream_hi));
     LG_CUDA(c, cudaEventRecord(s->ev_done, c->hash_stream_hi));
     LG_CUDA(c, cudaStreamWaitEvent(c->stream, s->ev_done, 0));
   } else {
-    LG_TRY(encode_runs(s, local, s->rho, s->peer_u, true, nullptr));
+    LG_TRY(encode_runs(s, local, s->rho, s->peer_u, true, nullptr, 0));
     LG_TRY(post(s, c->stream, 0, nullptr, 0));  // every rank's rows have been stored ...
     LG_TRY(wait_all(s, c->stream));             // ... everywhere
     LG_TRY(hash_columns(c, m.u, m.rows, m.log_k, m.rho_inv, m.leaves, s->ctx->col_len_prefix));
@@ -522,7 +540,7 @@ static int lg_shard_create_impl(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_in
   while (((size_t)1 << s->log_n_local) < s->n_local) s->log_n_local++;
   s->t_max = t_max;
   s->sub = sub_blocks;
-  if (const char* e = getenv("LG_SHARD_PIPELINE")) s->pipeline = atoi(e) != 0 ? 1 : 0;
+  if (const char* e = getenv("LG_SHARD_PIPELINE")) s->pipeline = atoi(e) < 0 ? -1 : (atoi(e) > 2 ? 2 : atoi(e));
   build_runs(s);
   int st = lg_matrix_create(ctx, s->rows, s->kg, rho_inv, &s->cols);
   if (st == OK && t_max) st = lg_matrix_create(ctx, s->rows, s->kg, 2, &s->rhat);
@@ -537,6 +555,8 @@ static int lg_shard_create_impl(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_in
     if (e == cudaSuccess) e = cudaMemset(s->mail, 0, s->mail_bytes);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_step, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_local[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_local[1], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->host_pin, kMailHeader, cudaHostAllocDefault);
     if (e == cudaSuccess && !c->hash_stream_hi) {
       int lo = 0, hi = 0;
@@ -587,6 +607,8 @@ int lg_shard_free(lg_shard* s) {
   if (s->host_pin) cudaFreeHost(s->host_pin);
   if (s->ev_step) cudaEventDestroy(s->ev_step);
   if (s->ev_done) cudaEventDestroy(s->ev_done);
+  for (int i = 0; i < 2; i++)
+    if (s->ev_local[i]) cudaEventDestroy(s->ev_local[i]);
   delete s;
   return OK;
 }
@@ -666,7 +688,7 @@ int lg_shard_connect_local(lg_shard* const* shards, int world) {
 
 int lg_shard_set_pipeline(lg_shard* s, int enabled) {
   if (!s) return ERR_INVALID;
-  s->pipeline = enabled < 0 ? -1 : (enabled != 0 ? 1 : 0);
+  s->pipeline = enabled < 0 ? -1 : (enabled > 2 ? 2 : enabled);
   return OK;
 }
 
@@ -750,7 +772,7 @@ static int lg_shard_prove_matrix_impl(lg_shard* s, lg_ligero* L, const uint64_t*
     LG_CUDA(c, cudaGetLastError());
   }
   cudaFreeAsync(d_ra, c->stream);
-  LG_TRY(encode_runs(s, (const uint64_t*)d_ra_local, 2, s->peer_rhat, false, nullptr));
+  LG_TRY(encode_runs(s, (const uint64_t*)d_ra_local, 2, s->peer_rhat, false, nullptr, 0));
   if (d_ra_local) cudaFreeAsync(d_ra_local, c->stream);
   LG_TRY(post(s, c->stream, 0, nullptr, 0));
   LG_TRY(wait_all(s, c->stream));

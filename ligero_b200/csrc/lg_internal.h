@@ -98,6 +98,9 @@ struct Ctx {
   // one priority step ABOVE the context stream -- a column's BLAKE2s chain is latency bound, so its few warps must be
   // resident and scheduled first; the encoder fills the rest of the SM
   cudaStream_t hash_stream_hi = nullptr;
+  // when set, encode_rows records this event right after launching the shared-memory kernel, i.e. before the last
+  // strided pass (the NVLink-bound scatter of a sharded encode): the multi-GPU pipeline starts a block's column hash there
+  cudaEvent_t ev_after_local = nullptr;
   cudaStream_t hash_stream = nullptr;
   cudaEvent_t ev_encoded = nullptr, ev_hashed = nullptr;
   uint32_t* hash_state = nullptr;

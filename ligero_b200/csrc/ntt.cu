@@ -813,6 +813,7 @@ int encode_rows(Ctx* ctx, const Fr* msg, size_t rows, int log_k, int rho_inv, Fr
     LG_TRY(launch_local<0>(ctx, a));
   }
   phase_mark(ctx, PH_NTT_LOCAL);
+  if (ctx->ev_after_local) LG_CUDA(ctx, cudaEventRecord(ctx->ev_after_local, ctx->stream));
   if (q > l && rho_inv > 1) {
     Fr* p = cosets;
     const size_t prow = rows * (size_t)(rho_inv - 1);

@@ -182,9 +182,10 @@ class ShardedCommitter:
         self.subtree_roots = None
 
     def set_pipeline(self, enabled):
-        """True / False, or None for the library default (by world size).  Same setting on every rank."""
+        """0 / False: off; 1 / True: eager (hash beside the next block's shared-memory kernel); 2: deferred (hash beside the
+        next block's NVLink-bound last pass); None: the library default by world size.  Same setting on every rank."""
         from .backend import check
-        v = -1 if enabled is None else int(bool(enabled))
+        v = -1 if enabled is None else int(enabled)
         check(self.ctx.lib.lg_shard_set_pipeline(self.handle, v), self.ctx.handle, "lg_shard_set_pipeline")
 
     def close(self):
@@ -222,7 +223,7 @@ class ShardedCommitter:
         """bench.py's N > 1 path: strong scaling of one R x k encode+commit over `world` GPUs.  Every rank generates its
         own rows of the SAME seeded matrix (ligero_b200.synthetic), so the root is the one N = 1 and the CPU oracle get."""
         from .synthetic import matrix_rows_torch
-        pipeline = {"0": False, "1": True}.get(os.environ.get("LG_MGPU_PIPELINE", ""), None)
+        pipeline = {"0": 0, "1": 1, "2": 2}.get(os.environ.get("LG_MGPU_PIPELINE", ""), None)
         sub = int(os.environ.get("LG_MGPU_SUB", "1"))
         m = R // 4
         sc = ShardedCommitter(ctx, m, k, rho, rank, world, pipeline, sub)
@@ -268,7 +269,7 @@ class ShardedCommitter:
         host = torch.empty_like(msg, device="cpu").pin_memory()
         host.copy_(msg)
         if pipeline is None and "LG_SHARD_PIPELINE" not in os.environ:
-            sc.set_pipeline(True)        # host input: the upload paces the encoder, hashing behind it is free
+            sc.set_pipeline(int(os.environ.get("LG_MGPU_E2E_PIPELINE", "1")))   # host input: the upload paces the encoder
         sc.commit(host)
         dist.barrier()
         torch.cuda.synchronize()
@@ -298,8 +299,8 @@ class ShardedCommitter:
             "root_check": ("equals the CPU-oracle root of the whole matrix (tests/golden/full_size_root.json)"
                            if expected_root is not None else "no pinned root for this shape"),
             "kernel_ms_rank0": kernel_ms, "kernel_launches_rank0": kernel_launches, "rows_per_rank": rows_g,
-            "hash_pipeline": (bool(pipeline) if pipeline is not None else
-                              (os.environ["LG_SHARD_PIPELINE"] != "0" if "LG_SHARD_PIPELINE" in os.environ else world >= 4)),
+            "hash_pipeline": (int(pipeline) if pipeline is not None else
+                              (int(os.environ["LG_SHARD_PIPELINE"]) if "LG_SHARD_PIPELINE" in os.environ else (2 if world >= 4 else 0))),
         }
 
 

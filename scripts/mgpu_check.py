@@ -21,7 +21,7 @@ for (m, k, rho) in [(3, 8, 8), (5, 64, 8), (86, 128, 8), (33, 2048, 8), (9, 8192
     full[:, 3] &= (1 << 60) - 1
     want = cref.commit(full, 4 * m, k, rho)["root"] if rank == 0 else None
     got = []
-    for pipe, sub in ((True, 1), (False, 1), (True, 3)):
+    for pipe, sub in ((1, 1), (0, 1), (2, 1), (2, 3)):
         sc = par.ShardedCommitter(ctx, m, k, rho, rank, world, pipe, sub)
         local = np.ascontiguousarray(full.reshape(4 * m, k, 4)[sc.row_ids]).reshape(-1, 4) if sc.rows_g else np.zeros((k, 4), np.uint64)
         dev = torch.from_numpy(local.view(np.int64)).cuda()
@@ -33,7 +33,7 @@ for (m, k, rho) in [(3, 8, 8), (5, 64, 8), (86, 128, 8), (33, 2048, 8), (9, 8192
         sc.close()
     if rank == 0:
         same = all(r == want for r in got)
-        print(f"m={m} k={k} rho={rho} world={world}: {len(got)} sharded roots (pipelined / plain / 3 sub-blocks; device, pinned "
+        print(f"m={m} k={k} rho={rho} world={world}: {len(got)} sharded roots (eager / plain / deferred / deferred with 3 sub-blocks; device, pinned "
               f"and pageable input) {'==' if same else '!='} oracle root", flush=True)
         ok &= same
     dist.barrier()

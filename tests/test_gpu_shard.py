@@ -20,7 +20,7 @@ def rand_matrix(rows, k, seed):
 
 
 @pytest.mark.parametrize("m,k,rho", [(3, 8, 8), (5, 64, 8), (86, 128, 8), (33, 2048, 8), (9, 8192, 4), (2, 4096, 2)])
-@pytest.mark.parametrize("pipeline,sub", [(True, 1), (False, 1), (True, 2), (True, 3)])
+@pytest.mark.parametrize("pipeline,sub", [(1, 1), (0, 1), (1, 2), (2, 1), (2, 3)])
 def test_shard_commit_world1_equals_oracle_root(gpu_ctx, m, k, rho, pipeline, sub):
     import torch
     full = rand_matrix(4 * m, k, 100 + m)
