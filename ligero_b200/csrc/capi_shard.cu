@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(1024) shard_post_kernel(Peers peers, int world
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
-    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers.mail[threadIdx.x] + kMailFlags);
-    f[me] = epoch;
+    // max, not store: with two encode streams a later run's flag may be raised before an earlier one's
+    atomicMax_system(reinterpret_cast<unsigned long long*>(peers.mail[threadIdx.x] + kMailFlags) + me, epoch);
   }
 }
 
@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(256) shard_post_paths_kernel(Peers peers, int 
   __threadfence_system();
   __syncthreads();
   if ((int)threadIdx.x < world) {
-    volatile unsigned long long* f = reinterpret_cast<volatile unsigned long long*>(peers.mail[threadIdx.x] + kMailFlags);
-    f[me] = epoch;
+    // max, not store: with two encode streams a later run's flag may be raised before an earlier one's
+    atomicMax_system(reinterpret_cast<unsigned long long*>(peers.mail[threadIdx.x] + kMailFlags) + me, epoch);
   }
 }
 
@@ -175,6 +175,15 @@ struct lg_shard {
   unsigned long long epoch = 0;
   Fr* scratch = nullptr;       // coset intermediate of one run (k > 1024)
   size_t scratch_bytes = 0;
+  // two-stream encoding (odd runs on alt_stream): the NVLink-bound last pass of run j overlaps the shared-memory kernel
+  // of run j+1; needs its own coset intermediate and its own NTT temporary (Ctx::scratch is swapped per run)
+  int two_stream = -1;         // -1: by world size
+  cudaStream_t alt_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  Fr* scratch2 = nullptr;
+  size_t scratch2_bytes = 0;
+  void* ctx_scratch2 = nullptr;
+  size_t ctx_scratch2_bytes = 0;
   cudaEvent_t ev_step = nullptr, ev_done = nullptr, ev_local[2] = {nullptr, nullptr};
   uint8_t* host_pin = nullptr; // pinned: header read-back (roots, err)
   uint32_t* local_src_rows = nullptr;  // device: global row of every local row (gather of r_a / the witness)
@@ -239,18 +248,20 @@ int check_err(lg_shard* s) {  // after a stream synchronisation
   return OK;
 }
 
-int ensure_scratch(lg_shard* s, size_t bytes) {
+int ensure_buf(lg_shard* s, Fr** buf, size_t* have, size_t bytes) {
   Ctx* c = &s->ctx->c;
-  if (bytes <= s->scratch_bytes) return OK;
+  if (bytes <= *have) return OK;
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (s->scratch) cudaFree(s->scratch);
-  s->scratch = nullptr;
-  s->scratch_bytes = 0;
-  cudaError_t e = cudaMalloc(&s->scratch, bytes);
+  if (s->alt_stream) LG_CUDA(c, cudaStreamSynchronize(s->alt_stream));
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  cudaError_t e = cudaMalloc(buf, bytes);
   if (e != cudaSuccess) return sfail(s, ERR_NOMEM, std::string("shard scratch cudaMalloc: ") + cudaGetErrorString(e));
-  s->scratch_bytes = bytes;
+  *have = bytes;
   return OK;
 }
+int ensure_scratch(lg_shard* s, size_t bytes) { return ensure_buf(s, &s->scratch, &s->scratch_bytes, bytes); }
 
 // encode every run of `local` (host or device, the rank's rows in run order) into the peers' shards `dst`.
 // hash != nullptr: the block pipeline -- a flag after every run, and the owner hashes block j on its hash stream
@@ -274,20 +285,67 @@ int encode_runs(lg_shard* s, const uint64_t* local, uint32_t rho, void* const* d
                               c->hash_state, hash->m.leaves, s->ctx->col_len_prefix);
   };
   unsigned long long prev_epoch = 0;
+  // two streams (device input, rows longer than one chunk, eager or no hashing): odd runs go to alt_stream
+  const int ts_default = s->world >= 4 ? 1 : 0;
+  const bool two = (s->two_stream < 0 ? ts_default : s->two_stream) != 0 && mode != 2 && s->log_k > 10 && s->runs.size() > 1 &&
+                   (!local || is_device_ptr(local));
+  cudaStream_t main_stream = c->stream;
+  void* ctx_scr = c->scratch;
+  size_t ctx_scr_bytes = c->scratch_bytes;
+  if (two) {
+    if (!s->alt_stream) {
+      int prio = 0;
+      LG_CUDA(c, cudaStreamGetPriority(main_stream, &prio));
+      LG_CUDA(c, cudaStreamCreateWithPriority(&s->alt_stream, cudaStreamNonBlocking, prio));
+      LG_CUDA(c, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+      LG_CUDA(c, cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
+    LG_TRY(ensure_buf(s, &s->scratch2, &s->scratch2_bytes, (size_t)(rho - 1) * s->max_run * s->k * sizeof(Fr)));
+    LG_TRY(ensure_buf(s, (Fr**)&s->ctx_scratch2, &s->ctx_scratch2_bytes, s->max_run * s->k * sizeof(Fr)));
+    LG_CUDA(c, cudaEventRecord(s->ev_fork, main_stream));
+    LG_CUDA(c, cudaStreamWaitEvent(s->alt_stream, s->ev_fork, 0));
+  }
+  auto restore = [&]() {
+    if (two) {  // hand the (possibly grown) NTT temporary back and rejoin the streams
+      if (c->stream == s->alt_stream) {
+        s->ctx_scratch2 = c->scratch;
+        s->ctx_scratch2_bytes = c->scratch_bytes;
+      } else {
+        ctx_scr = c->scratch;
+        ctx_scr_bytes = c->scratch_bytes;
+      }
+      c->stream = main_stream;
+      c->scratch = ctx_scr;
+      c->scratch_bytes = ctx_scr_bytes;
+    }
+  };
   for (size_t j = 0; j < s->runs.size(); j++) {
     const Run& r = s->runs[j];
-    if (hash && mode == 1 && s->world > 1 && groups_saved == 3) c->persist_groups = (j == 0) ? 3 : overlap_groups;
+    if (hash && mode == 1 && groups_saved == 3) c->persist_groups = (j == 0) ? 3 : overlap_groups;
     cudaEvent_t ev_loc = s->ev_local[j & 1];
     if (hash && mode == 2) c->ev_after_local = ev_loc;
+    Fr* coset_scratch = s->scratch;
+    if (two) {
+      restore();
+      if (j & 1) {
+        c->stream = s->alt_stream;
+        c->scratch = s->ctx_scratch2;
+        c->scratch_bytes = s->ctx_scratch2_bytes;
+        coset_scratch = s->scratch2;
+      }
+    }
     int st = OK;
     if (r.nrows)
       st = lg_encode_sharded_rows(s->ctx, local + r.local_off * s->k * 4, r.nrows, r.row_base, s->rows, s->k, rho, dst, s->world,
-                                  (uint64_t*)s->scratch, plain ? 1 : 0);
+                                  (uint64_t*)coset_scratch, plain ? 1 : 0);
     else if (hash && mode == 2)
       st = cudaEventRecord(ev_loc, c->stream) == cudaSuccess ? OK : ERR_CUDA;
     c->persist_groups = groups_saved;
     c->ev_after_local = nullptr;
-    LG_TRY(st);
+    if (st != OK) {
+      restore();
+      return st;
+    }
     if (hash) {
       s->epoch++;
       shard_post_kernel<<<1, 32, 0, c->stream>>>(s->peers, s->world, s->rank, 0, nullptr, 0, s->epoch);
@@ -302,6 +360,11 @@ int encode_runs(lg_shard* s, const uint64_t* local, uint32_t rho, void* const* d
         LG_TRY(hash_block(r, s->epoch, s->ev_step));
       }
     }
+  }
+  if (two) {
+    restore();
+    LG_CUDA(c, cudaEventRecord(s->ev_join, s->alt_stream));
+    LG_CUDA(c, cudaStreamWaitEvent(main_stream, s->ev_join, 0));
   }
   return OK;
 }
@@ -540,6 +603,7 @@ static int lg_shard_create_impl(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_in
   while (((size_t)1 << s->log_n_local) < s->n_local) s->log_n_local++;
   s->t_max = t_max;
   s->sub = sub_blocks;
+  if (const char* e = getenv("LG_SHARD_TWO_STREAM")) s->two_stream = atoi(e) != 0 ? 1 : 0;
   if (const char* e = getenv("LG_SHARD_PIPELINE")) s->pipeline = atoi(e) < 0 ? -1 : (atoi(e) > 2 ? 2 : atoi(e));
   build_runs(s);
   int st = lg_matrix_create(ctx, s->rows, s->kg, rho_inv, &s->cols);
@@ -601,6 +665,14 @@ int lg_shard_free(lg_shard* s) {
   if (s->rhat) lg_matrix_free(s->rhat);
   if (s->mail) cudaFree(s->mail);
   if (s->scratch) cudaFree(s->scratch);
+  if (s->scratch2) cudaFree(s->scratch2);
+  if (s->ctx_scratch2) cudaFree(s->ctx_scratch2);
+  if (s->alt_stream) {
+    cudaStreamSynchronize(s->alt_stream);
+    cudaStreamDestroy(s->alt_stream);
+    cudaEventDestroy(s->ev_fork);
+    cudaEventDestroy(s->ev_join);
+  }
   if (s->local_src_rows) cudaFree(s->local_src_rows);
   if (s->pre_full) cudaFree(s->pre_full);
   if (s->pre_local) cudaFree(s->pre_local);

@@ -90,7 +90,7 @@ struct Ctx {
   // commit pipeline: column hashing of row tile i (high-priority stream) overlaps the encoding of tile i+1
   double last_shoup_peak[2] = {0, 0};  // lg_bench_int_peak: table-constant products/s, lazy butterflies/s
   bool overlap = true;
-  // groups of 256 threads per SM in the persistent encoder (ntt.cu): 3 = every register of the SM, 2 = capped at 88
+  // groups of 256 threads per SM in the persistent encoder (ntt.cu): 3 = every register of the SM, 2 = capped at 80
   // registers so that four CTAs of a co-resident column-hash kernel fit beside it (multi-GPU block pipeline);
   // 0 = the one-CTA-per-chunk kernel.  LG_NTT_PERSIST=0 / LG_NTT_GROUPS=2 in the environment set the default.
   int persist_groups = 3;

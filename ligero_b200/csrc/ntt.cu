@@ -443,10 +443,11 @@ __device__ __forceinline__ void pass4_inplace(uint4* buf, int s, uint32_t t, uin
   for (int e = 0; e < 4; e++) sts4(buf, base | ((uint32_t)e << s), x[e]);
 }
 
-// CAPPED: at most 88 registers per thread (two groups: 45 K of the SM's 64 K registers, the rest is left to a co-resident
-// column-hash kernel -- the multi-GPU block pipeline of capi_shard.cu)
+// CAPPED: at most 80 registers per thread (two groups: 40 K of the SM's 64 K registers; four 64-thread CTAs of the column-hash
+// kernel at 80 registers take 20 K more -- with 88 registers the sum was exactly 64 K and the hash CTAs never became co-resident;
+// the multi-GPU block pipeline of capi_shard.cu)
 template <int GROUPS, bool CAPPED>
-__global__ void __launch_bounds__(GROUPS* kPT, 1) __maxnreg__(CAPPED ? 88 : 255)
+__global__ void __launch_bounds__(GROUPS* kPT, 1) __maxnreg__(CAPPED ? 80 : 255)
     ntt_persist_kernel(const __grid_constant__ LocalArgs a) {
   extern __shared__ uint4 smem[];
   // one copy of the order-1024 twiddles per SM
@@ -722,6 +723,11 @@ static int launch_persist_g(Ctx* ctx, const LocalArgs& a) {
   const void* fn = (const void*)ntt_persist_kernel<GROUPS, CAPPED>;
   if (!ctx->smem_configured.count(fn)) {  // per device: one process may drive several GPUs
     LG_CUDA(ctx, cudaFuncSetAttribute(ntt_persist_kernel<GROUPS, CAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // Ask for the largest shared-memory carve-out.  The driver otherwise picks the smallest configuration that holds
+    // this CTA (164 KiB for two groups), which leaves ~2 KiB: not one CTA of a co-resident column-hash kernel (3.3 KiB
+    // + 1 KiB reserved) fits, and the two kernels serialise although registers and warps are free.
+    LG_CUDA(ctx, cudaFuncSetAttribute(ntt_persist_kernel<GROUPS, CAPPED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
     ctx->smem_configured.insert(fn);
   }
   const unsigned long long chunks = a.total >> kLogPE;

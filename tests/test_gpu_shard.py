@@ -41,6 +41,26 @@ def test_shard_commit_world1_equals_oracle_root(gpu_ctx, m, k, rho, pipeline, su
         sc.close()
 
 
+@pytest.mark.parametrize("pipeline", [0, 1])
+def test_two_stream_encoding_world1(gpu_ctx, pipeline, monkeypatch):
+    """odd runs on a second stream (the multi-GPU default from 4 GPUs): same root, flags raised out of order are fine"""
+    import torch
+    monkeypatch.setenv("LG_SHARD_TWO_STREAM", "1")
+    for (m, k, rho, sub) in [(33, 2048, 8, 1), (9, 8192, 4, 2), (40, 4096, 8, 3)]:
+        full = rand_matrix(4 * m, k, 7 + m)
+        want = cref.commit(full, 4 * m, k, rho)["root"]
+        sc = par.ShardedCommitter(gpu_ctx, m, k, rho, 0, 1, pipeline, sub)
+        try:
+            local = np.ascontiguousarray(full.reshape(4 * m, k, 4)[sc.row_ids]).reshape(-1, 4)
+            dev = torch.from_numpy(local.view(np.int64)).cuda()
+            for _ in range(4):
+                sc.commit_async(dev)
+            assert sc.root() == want
+            assert sc.commit(local) == want           # host input falls back to one stream
+        finally:
+            sc.close()
+
+
 def test_shard_layout_matches_python_mirror(gpu_ctx):
     from ctypes import byref, c_size_t
     for (m, world, sub) in [(7, 1, 1), (7, 1, 3), (10, 1, 4)]:
