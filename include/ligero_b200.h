@@ -320,7 +320,7 @@ int lg_proof_deserialize(const uint8_t* buf, size_t len, lg_proof** out);
 typedef struct lg_shard lg_shard;
 /* m, k, rho_inv: shape of the commitment (4m rows); t_max: openings per test (0: commitment only, no prover
  * buffers); sub_blocks >= 1: each of the X, Y, Z, W blocks is encoded in that many pipeline steps (see
- * lg_shard_layout).  world a power of two <= 8, k divisible by world. */
+ * lg_shard_layout), 0: chosen by world size (4 at 8 GPUs, else 1).  world a power of two <= 8, k divisible by world. */
 int lg_shard_create(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_inv, int rank, int world, size_t t_max, int sub_blocks,
                     lg_shard** out);
 int lg_shard_free(lg_shard* s);
@@ -330,8 +330,9 @@ int lg_shard_handles(lg_shard* s, uint8_t out[192]);
 int lg_shard_connect(lg_shard* s, const uint8_t* all_handles);
 /* the same for shards that live in ONE process (enables peer access between their devices) */
 int lg_shard_connect_local(lg_shard* const* shards, int world);
-/* hash the row blocks that have arrived behind the encoding of the next: 1 on, 0 off, -1 (default) by world size
- * (on from 4 GPUs, where a rank's column hash is a latency chain; LG_SHARD_PIPELINE=0/1 in the environment overrides).
+/* hash the row blocks that have arrived behind the encoding of the next: 0 off, 1 eager (beside the next block's
+ * shared-memory kernel), 2 deferred (beside the next block's last strided pass), -1 (default) by world size: eager at
+ * 8 GPUs, where a rank's column hash is a latency chain, off below (LG_SHARD_PIPELINE in the environment overrides).
  * Every rank of a group must use the same setting. */
 int lg_shard_set_pipeline(lg_shard* s, int enabled);
 /* This rank's rows: 4*sub_blocks runs of consecutive global rows, in the order its local matrix stores them

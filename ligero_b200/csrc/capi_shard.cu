@@ -286,7 +286,7 @@ int encode_runs(lg_shard* s, const uint64_t* local, uint32_t rho, void* const* d
   };
   unsigned long long prev_epoch = 0;
   // two streams (device input, rows longer than one chunk, eager or no hashing): odd runs go to alt_stream
-  const int ts_default = s->world >= 4 ? 1 : 0;
+  const int ts_default = (s->world >= 8 && hash) ? 1 : 0;
   const bool two = (s->two_stream < 0 ? ts_default : s->two_stream) != 0 && mode != 2 && s->log_k > 10 && s->runs.size() > 1 &&
                    (!local || is_device_ptr(local));
   cudaStream_t main_stream = c->stream;
@@ -374,11 +374,14 @@ int commit_async(lg_shard* s, const uint64_t* local) {
   if (!s->connected) return sfail(s, ERR_STATE, "lg_shard_connect first");
   if (!local && s->rows_local) return sfail(s, ERR_INVALID, "null input matrix");
   Matrix& m = s->cols->m;
-  // Measured on B200 (2^24-gate shape): with 2 GPUs a rank owns 32 768 columns, its hash saturates the ALU pipe and
-  // sharing the SMs with it costs the encoder more than the overlap saves (77 vs 67 ms per step); from 4 GPUs on the
-  // hash is a latency chain over few columns and runs behind the encoder.  Host input is the exception: the upload
-  // makes the encoder wait anyway (lg_shard_set_pipeline(1) there: 79 vs 89 ms end to end at 2 GPUs).
-  const int pipe = s->pipeline < 0 ? (s->world >= 4 ? 2 : 0) : s->pipeline;
+  // Measured on 8 x B200 (2^24-gate shape, ms per step; profiles/r2_mgpu_sweep.txt):
+  //   2 GPUs: a rank owns 32 768 columns, its hash saturates the ALU pipe and sharing the SMs with it costs the encoder more
+  //           than the overlap saves (77 pipelined vs 67 plain);   4 GPUs: 40.6 vs 38.7, still a loss;
+  //   8 GPUs: the hash is a 7.5 ms latency chain over 8 192 columns; eager pipeline + two encode streams + 16 steps: 21.5
+  //           vs 25.0 plain (eager alone 26.3, two streams alone 24.5, deferred 26.3).
+  // Host input is the exception at every size: the upload paces the encoder anyway (lg_shard_set_pipeline(1): 79 vs 89 ms
+  // end to end at 2 GPUs, 39 vs 46 at 8).
+  const int pipe = s->pipeline < 0 ? (s->world >= 8 ? 1 : 0) : s->pipeline;
   if (pipe) {
     LG_TRY(hash_pipeline_setup(c, m.n));
     // the hash stream must not start on a new commitment before the previous one's consumers are done
@@ -585,7 +588,11 @@ static int lg_shard_create_impl(lg_ctx* ctx, size_t m, size_t k, uint32_t rho_in
     return set_error(c, ERR_INVALID, "world must be a power of two <= 8 and 0 <= rank < world");
   if (m == 0 || k < 2 || (k & (k - 1)) || k % world || rho_inv < 2 || (rho_inv & (rho_inv - 1)) || (rho_inv * k / world) < 2)
     return set_error(c, ERR_INVALID, "shape not shardable: k a power of two divisible by world, rho_inv a power of two >= 2");
-  if (sub_blocks < 1) sub_blocks = 1;
+  if (sub_blocks < 1) {  // automatic: the eager pipeline of 8 GPUs wants finer steps (measured 23.1 ms with 4 steps, 21.9 with 8, 21.5 with 16)
+    sub_blocks = world >= 8 ? 4 : 1;
+    if (const char* e = getenv("LG_SHARD_SUB"))
+      if (atoi(e) >= 1) sub_blocks = atoi(e);
+  }
   if ((size_t)sub_blocks > m) sub_blocks = (int)m;
   lg_shard* s = new (std::nothrow) lg_shard();
   if (!s) return ERR_NOMEM;
@@ -945,7 +952,7 @@ lg_ctx* lg_mgpu_ctx(lg_mgpu* g, int i) { return (g && i >= 0 && i < g->world) ? 
 static int lg_mgpu_commit_impl(lg_mgpu* g, const uint64_t* preenc_u, size_t rows, size_t k, uint32_t rho_inv, uint8_t root_out[32]) {
   if (!g || !preenc_u || rows % 4) return ERR_INVALID;
   lg_shard* sh[kMaxRanks] = {};
-  int st = on_all(g, [&](int i) { return lg_shard_create(g->ctx[i], rows / 4, k, rho_inv, i, g->world, 0, 1, &sh[i]); });
+  int st = on_all(g, [&](int i) { return lg_shard_create(g->ctx[i], rows / 4, k, rho_inv, i, g->world, 0, 0, &sh[i]); });
   if (st == OK) st = lg_shard_connect_local(sh, g->world);
   if (st == OK) {
     uint8_t roots[kMaxRanks][32];
@@ -977,7 +984,7 @@ static int lg_mgpu_ligero_new_impl(lg_mgpu* g, const lg_circuit* circuit, const 
     LG_TRY(lg_ligero_set_trace_mode(ml->L[i], 1));
     size_t m, k, n, t;
     LG_TRY(lg_ligero_params(ml->L[i], &m, &k, &n, &t, nullptr));
-    return lg_shard_create(g->ctx[i], m, k, (uint32_t)(n / k), i, g->world, t, 1, &ml->sh[i]);
+    return lg_shard_create(g->ctx[i], m, k, (uint32_t)(n / k), i, g->world, t, 0, &ml->sh[i]);
   });
   if (st == OK) st = lg_shard_connect_local(ml->sh, g->world);
   if (st != OK) {

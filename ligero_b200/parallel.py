@@ -164,14 +164,17 @@ class ShardedCommitter:
     `pipeline` (default on): the X, Y, Z, W row blocks (times `sub_blocks`) are encoded one after the other and the
     column owner hashes each block, on a higher-priority stream, while the next one is encoded and delivered."""
 
-    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int, pipeline=None, sub_blocks: int = 1, t_max: int = 0):
+    def __init__(self, ctx, m: int, k: int, rho: int, rank: int, world: int, pipeline=None, sub_blocks: int = 0, t_max: int = 0):
         assert world & (world - 1) == 0 and k % world == 0 and (rho * k // world) >= 2
+        from ctypes import byref, c_size_t
         from .backend import CommittedMatrix, check
         self.ctx, self.m, self.k, self.rho, self.rank, self.world = ctx, m, k, rho, rank, world
-        self.sub_blocks = sub_blocks
+        self.handle = _make_shard(ctx, m, k, rho, rank, world, t_max, sub_blocks)     # sub_blocks = 0: the library's choice
+        nr = c_size_t()
+        check(ctx.lib.lg_shard_layout(self.handle, None, byref(nr), None, None), ctx.handle, "lg_shard_layout")
+        self.sub_blocks = sub_blocks = nr.value // 4
         self.row_ids = local_row_ids(m, world, rank, sub_blocks)
         self.rows_g, self.kg = len(self.row_ids), k // world
-        self.handle = _make_shard(ctx, m, k, rho, rank, world, t_max, sub_blocks)
         self.pipeline = pipeline
         if pipeline is not None:
             self.set_pipeline(pipeline)
@@ -224,7 +227,7 @@ class ShardedCommitter:
         own rows of the SAME seeded matrix (ligero_b200.synthetic), so the root is the one N = 1 and the CPU oracle get."""
         from .synthetic import matrix_rows_torch
         pipeline = {"0": 0, "1": 1, "2": 2}.get(os.environ.get("LG_MGPU_PIPELINE", ""), None)
-        sub = int(os.environ.get("LG_MGPU_SUB", "1"))
+        sub = int(os.environ.get("LG_MGPU_SUB", "0"))
         m = R // 4
         sc = ShardedCommitter(ctx, m, k, rho, rank, world, pipeline, sub)
         dev = sc.dev
@@ -281,7 +284,7 @@ class ShardedCommitter:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         assert r == root0
         e2e_ms = float(dt.item()) * 1e3 / args.steps
-        rows_g = sc.rows_g
+        rows_g, sub = sc.rows_g, sc.sub_blocks
         sc.close()
         par = (f"rows/{world} encode (4x{sub} row blocks) with the column exchange fused into the encode kernels (NVLink peer "
                f"stores) -> column-range/{world} BLAKE2s of each block behind the encoding of the next -> subtree -> root "
@@ -300,7 +303,7 @@ class ShardedCommitter:
                            if expected_root is not None else "no pinned root for this shape"),
             "kernel_ms_rank0": kernel_ms, "kernel_launches_rank0": kernel_launches, "rows_per_rank": rows_g,
             "hash_pipeline": (int(pipeline) if pipeline is not None else
-                              (int(os.environ["LG_SHARD_PIPELINE"]) if "LG_SHARD_PIPELINE" in os.environ else (2 if world >= 4 else 0))),
+                              (int(os.environ["LG_SHARD_PIPELINE"]) if "LG_SHARD_PIPELINE" in os.environ else (1 if world >= 8 else 0))),
         }
 
 
@@ -311,7 +314,7 @@ class ShardedProver:
     its subtree.  Every rank runs the same Fiat-Shamir transcript, so all ranks end with the same proof, byte-identical
     to the single-GPU prover's (tests/test_gpu_multi.py) and through it to the oracle's."""
 
-    def __init__(self, ctx, ligero, rank: int, world: int, sub_blocks: int = 1):
+    def __init__(self, ctx, ligero, rank: int, world: int, sub_blocks: int = 0):
         self.ctx, self.L, self.rank, self.world = ctx, ligero, rank, world
         self.m, self.k, self.n, self.t = ligero.m, ligero.k, ligero.n, ligero.t
         self.rho = self.n // self.k
