@@ -163,6 +163,10 @@ typedef struct lg_constraints lg_constraints;
 int lg_constraints_create(lg_ctx* ctx, size_t mk, const uint32_t* col_ptr, const uint32_t* row_idx, const uint32_t* val_id,
                           size_t nnz, const uint64_t* const_table, size_t n_consts, lg_constraints** out);
 int lg_constraints_free(lg_constraints* a);
+/* read the CSC back (parity tests: the device builder of LigeroCircuit::new against the host builder); every output
+ * pointer is nullable; capacities: col_ptr mk+1, row_idx / val_id nnz, const_table Fr[n_consts] */
+int lg_constraints_read(const lg_constraints* a, size_t* mk, size_t* nnz, size_t* n_consts, uint32_t* col_ptr, uint32_t* row_idx,
+                        uint32_t* val_id, uint64_t* const_table);
 /* SparseMatrix::row_mul, src/matrices/mod.rs:100-110 (call mod.rs:722): out = r^T A, Fr[4mk] each */
 int lg_sparse_row_mul(lg_ctx* ctx, const lg_constraints* a, const uint64_t* r_linear, uint64_t* out);
 

@@ -80,6 +80,8 @@ SIGNATURES = {
     "lg_constraints_create": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t,
                                       POINTER(c_void_p)]),
     "lg_constraints_free": (c_int, [c_void_p]),
+    "lg_constraints_read": (c_int, [c_void_p, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t), c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "lg_sparse_row_mul": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "lg_linear_test": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_size_t)]),
     "lg_linear_test_seeded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_size_t)]),

@@ -339,6 +339,21 @@ class LigeroCircuit:
               self.ctx.handle, "device witness layout")
         return out
 
+    def constraints_csc(self):
+        """(col_ptr, row_idx, val_id, const_table) of the right-hand block of A as LigeroCircuit::new built it (read back
+        from the device; lg_constraints_read)"""
+        a = c_void_p()
+        check(self.lib.lg_ligero_constraints(self.handle, byref(a)), self.ctx.handle, "lg_ligero_constraints")
+        mk, nnz, nc = c_size_t(), c_size_t(), c_size_t()
+        check(self.lib.lg_constraints_read(a, byref(mk), byref(nnz), byref(nc), None, None, None, None), self.ctx.handle)
+        col_ptr = np.zeros(mk.value + 1, dtype=np.uint32)
+        row_idx = np.zeros(max(nnz.value, 1), dtype=np.uint32)
+        val_id = np.zeros(max(nnz.value, 1), dtype=np.uint32)
+        table = np.zeros((max(nc.value, 1), 4), dtype=np.uint64)
+        check(self.lib.lg_constraints_read(a, None, None, None, _ptr(col_ptr), _ptr(row_idx), _ptr(val_id), _ptr(table)),
+              self.ctx.handle, "lg_constraints_read")
+        return col_ptr, row_idx[: nnz.value], val_id[: nnz.value], table[: nc.value]
+
     def set_trace_mode(self, mode: int):
         """-1: device trace for wide circuits (default), 0: host evaluator, 1: device."""
         check(self.lib.lg_ligero_set_trace_mode(self.handle, mode), self.ctx.handle, "set_trace_mode")

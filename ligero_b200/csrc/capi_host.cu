@@ -201,14 +201,82 @@ void host_fft(std::vector<Fq>& a, bool inverse) {
 }
 
 // ---- constraint matrix (right-hand block of A) straight into CSC ------------------------------------
-struct Triplet {
-  uint32_t col, row, vid;
-};
+// value ids of the constants of the circuit: 0 -> +1, 1 -> -1, v >= 2 -> table[v - 2].  Canonical numbering shared by the
+// host and the device builder: constant nodes in node order, each registering its value c and then -c (an Add gate uses c,
+// a Mul gate -c: mod.rs:324-336, 343-355).  vidp / vidn are indexed like const_values.
+void constant_value_ids(const lg_circuit& c, std::vector<uint32_t>& vidp, std::vector<uint32_t>& vidn, std::vector<Fq>& table) {
+  std::map<Fq, uint32_t> ids;
+  const Fq minus_one = lgh::neg(lgh::kOne);
+  auto vid_of = [&](const Fq& v) -> uint32_t {
+    if (v == lgh::kOne) return 0;
+    if (v == minus_one) return 1;
+    auto it = ids.find(v);
+    if (it != ids.end()) return it->second;
+    const uint32_t id = (uint32_t)table.size() + 2;
+    table.push_back(v);
+    ids[v] = id;
+    return id;
+  };
+  vidp.assign(c.const_values.size(), 0);
+  vidn.assign(c.const_values.size(), 0);
+  std::vector<uint8_t> done(c.const_values.size(), 0);
+  for (const Node& nd : c.nodes)
+    if (nd.type == N_CONST && !done[nd.l]) {
+      done[nd.l] = 1;
+      vidp[nd.l] = vid_of(c.const_values[nd.l]);
+      vidn[nd.l] = vid_of(lgh::neg(c.const_values[nd.l]));
+    }
+}
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+bool debug_timing() {
+  const char* e = getenv("LG_DEBUG_TIMING");
+  return e && atoi(e) != 0;
+}
 
 int build_constraints(lg_ligero* L, std::string& err) {
   const lg_circuit& c = L->circuit;
   const auto& nodes = c.nodes;
   const size_t mk = L->m * L->k;
+  std::vector<uint32_t> vidp, vidn;
+  std::vector<Fq> table;
+  constant_value_ids(c, vidp, vidn, table);
+  // the reference panics on these (mod.rs:325, 345, 369-414): refuse them before building anything
+  for (size_t i = 0; i < nodes.size(); i++) {
+    const Node& nd = nodes[i];
+    if ((nd.type == N_ADD || nd.type == N_MUL) && nodes[nd.l].type == N_CONST && nodes[nd.r].type == N_CONST) {
+      err = nd.type == N_ADD ? "Add(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:325)"
+                             : "Mul(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:345)";
+      return ERR_UNSUPPORTED;
+    }
+  }
+  for (size_t o : L->outputs) {
+    const Node& nd = nodes[o];
+    if (nd.type != N_ADD && nd.type != N_MUL) {
+      err = "The output node must be an addition or multiplication gate";
+      return ERR_INVALID;
+    }
+  }
+  // large circuits: CSC built on the device (constraints.cu); LG_CSC_DEVICE=0 / 1 forces the host / device builder
+  bool on_device = nodes.size() >= ((size_t)1 << 16);
+  if (const char* e = getenv("LG_CSC_DEVICE")) on_device = atoi(e) != 0;
+  if (on_device) {
+    const double t0 = now_ms();
+    std::vector<uint8_t> type(nodes.size());
+    std::vector<uint32_t> l(nodes.size()), r(nodes.size()), outs(L->outputs.begin(), L->outputs.end());
+    for (size_t i = 0; i < nodes.size(); i++) {
+      type[i] = nodes[i].type;
+      l[i] = (uint32_t)nodes[i].l;
+      r[i] = (uint32_t)nodes[i].r;
+    }
+    const double t1 = now_ms();
+    const int s = lg::build_constraints_device(L->ctx, type.data(), l.data(), r.data(), nodes.size(), vidp.data(), vidn.data(), vidp.size(),
+                                               outs.data(), outs.size(), mk, table.empty() ? nullptr : (const uint64_t*)table.data(),
+                                               table.size(), &L->a);
+    if (debug_timing()) fprintf(stderr, "[lg] constraint matrix on the device: node arrays %.1f ms, build %.1f ms\n", t1 - t0, now_ms() - t1);
+    if (s != OK) err = lg_last_error(L->ctx);
+    return s;
+  }
   // index_map: node -> position after dropping every constant but node 0 (mod.rs:179-194)
   std::vector<uint32_t> index_map(nodes.size(), 0xffffffffu);
   index_map[0] = 0;
@@ -217,55 +285,40 @@ int build_constraints(lg_ligero* L, std::string& err) {
     if (nodes[i].type == N_CONST) seen++;
     else index_map[i] = (uint32_t)(i - seen);
   }
-  std::map<Fq, uint32_t> const_ids;
-  std::vector<Fq> table;
-  const Fq minus_one = lgh::neg(lgh::kOne);
-  auto vid_of = [&](const Fq& v) -> uint32_t {
-    if (v == lgh::kOne) return 0;
-    if (v == minus_one) return 1;
-    auto it = const_ids.find(v);
-    if (it != const_ids.end()) return it->second;
-    const uint32_t id = (uint32_t)table.size() + 2;
-    table.push_back(v);
-    const_ids[v] = id;
-    return id;
+  struct Triplet {
+    uint32_t col, row, vid;
   };
-  auto cval = [&](size_t node) { return c.const_values[nodes[node].l]; };
   std::vector<Triplet> trip;
   size_t row = 0;  // row inside each P matrix
-  auto add_gate = [&](size_t l, size_t r, uint32_t own_col) -> bool {  // P_add row
+  auto add_gate = [&](size_t l, size_t r, uint32_t own_col) {  // P_add row
     const bool lc = nodes[l].type == N_CONST, rc = nodes[r].type == N_CONST;
-    if (lc && rc) return false;
     const uint32_t base = (uint32_t)(3 * mk + row);
     if (lc) {
-      trip.push_back({0, base, vid_of(cval(l))});
+      trip.push_back({0, base, vidp[nodes[l].l]});
       trip.push_back({index_map[r], base, 0});
     } else if (rc) {
       trip.push_back({index_map[l], base, 0});
-      trip.push_back({0, base, vid_of(cval(r))});
+      trip.push_back({0, base, vidp[nodes[r].l]});
     } else {
       trip.push_back({index_map[l], base, 0});
       trip.push_back({index_map[r], base, 0});
     }
     trip.push_back({own_col, base, 1});
-    return true;
   };
-  auto mul_gate = [&](size_t l, size_t r, uint32_t own_col) -> bool {  // rows of -P_x, -P_y, -P_z
+  auto mul_gate = [&](size_t l, size_t r, uint32_t own_col) {  // rows of -P_x, -P_y, -P_z
     const bool lc = nodes[l].type == N_CONST, rc = nodes[r].type == N_CONST;
-    if (lc && rc) return false;
     const uint32_t rx = (uint32_t)row, ry = (uint32_t)(mk + row), rz = (uint32_t)(2 * mk + row);
     if (lc) {
-      trip.push_back({0, rx, vid_of(lgh::neg(cval(l)))});
+      trip.push_back({0, rx, vidn[nodes[l].l]});
       trip.push_back({index_map[r], ry, 1});
     } else if (rc) {
       trip.push_back({index_map[l], rx, 1});
-      trip.push_back({0, ry, vid_of(lgh::neg(cval(r)))});
+      trip.push_back({0, ry, vidn[nodes[r].l]});
     } else {
       trip.push_back({index_map[l], rx, 1});
       trip.push_back({index_map[r], ry, 1});
     }
     trip.push_back({own_col, rz, 1});
-    return true;
   };
   for (size_t i = 0; i < nodes.size(); i++) {
     const Node& nd = nodes[i];
@@ -274,17 +327,8 @@ int build_constraints(lg_ligero* L, std::string& err) {
       err = "internal: more rows than m*k";
       return ERR_STATE;
     }
-    if (nd.type == N_ADD) {
-      if (!add_gate(nd.l, nd.r, index_map[i])) {
-        err = "Add(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:325)";
-        return ERR_UNSUPPORTED;
-      }
-    } else if (nd.type == N_MUL) {
-      if (!mul_gate(nd.l, nd.r, index_map[i])) {
-        err = "Mul(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:345)";
-        return ERR_UNSUPPORTED;
-      }
-    }
+    if (nd.type == N_ADD) add_gate(nd.l, nd.r, index_map[i]);
+    else if (nd.type == N_MUL) mul_gate(nd.l, nd.r, index_map[i]);
     row++;
   }
   for (size_t o : L->outputs) {  // o = 1 for each output node (mod.rs:369-414)
@@ -293,21 +337,11 @@ int build_constraints(lg_ligero* L, std::string& err) {
       err = "internal: more rows than m*k";
       return ERR_STATE;
     }
-    bool ok;
-    if (nd.type == N_ADD) ok = add_gate(nd.l, nd.r, 0);
-    else if (nd.type == N_MUL) ok = mul_gate(nd.l, nd.r, 0);
-    else {
-      err = "The output node must be an addition or multiplication gate";
-      return ERR_INVALID;
-    }
-    if (!ok) {
-      err = "output gate with two constant operands is not supported (the reference panics)";
-      return ERR_UNSUPPORTED;
-    }
+    if (nd.type == N_ADD) add_gate(nd.l, nd.r, 0);
+    else mul_gate(nd.l, nd.r, 0);
     row++;
   }
-  // CSC by a counting sort on the column (stable: entries of a column keep the order in which the rows produced
-  // them, as a stable sort of the triplets would; 151 M entries at 2^24 gates)
+  // CSC by a counting sort on the column (stable: entries of a column keep the order in which the rows produced them)
   std::vector<uint32_t> col_ptr(mk + 1, 0), row_idx(trip.size()), val_id(trip.size());
   for (const auto& t : trip) col_ptr[t.col + 1]++;
   for (size_t cidx = 0; cidx < mk; cidx++) col_ptr[cidx + 1] += col_ptr[cidx];
@@ -1209,13 +1243,18 @@ static int lg_ligero_new_impl(lg_ctx* ctx, const lg_circuit* circuit, const size
     L->outputs.push_back(o);
   }
   std::string err;
+  const double t_c0 = now_ms();
   int s = build_constraints(L, err);
+  const double t_c1 = now_ms();
   if (s != OK) {
     if (!err.empty()) fail(ctx, s, err);
     lg_ligero_free(L);
     return s;
   }
   s = build_trace(L);
+  if (debug_timing())
+    fprintf(stderr, "[lg] LigeroCircuit::new: constraint matrix %.1f ms, trace schedule %.1f ms (%zu nodes)\n", t_c1 - t_c0, now_ms() - t_c1,
+            c.nodes.size());
   if (s != OK) {
     lg_ligero_free(L);
     return s;

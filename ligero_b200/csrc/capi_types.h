@@ -24,3 +24,10 @@ struct lg_constraints {
 namespace lg {
 bool is_device_ptr(const void* p);
 }
+
+// constraints.cu: CSC of the right-hand block of A built on the device from host node arrays
+namespace lg {
+int build_constraints_device(lg_ctx* ctx, const uint8_t* type, const uint32_t* l, const uint32_t* r, size_t n, const uint32_t* vidp,
+                             const uint32_t* vidn, size_t n_const_values, const uint32_t* outputs, size_t n_out, size_t mk,
+                             const uint64_t* const_table, size_t n_table, lg_constraints** out);
+}
