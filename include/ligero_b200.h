@@ -15,6 +15,11 @@
  *     parameter says otherwise; output pointers are host memory unless named `*_dev`;
  *   - a context owns one CUDA stream; calls on one context are stream-ordered and the functions that
  *     return host data synchronise that stream before returning.  One context per host thread;
+ *   - LIFETIMES: a context outlives everything created from it (lg_matrix, lg_constraints, lg_ligero, lg_shard): their free
+ *     functions use the context's stream, so destroy the children first, the context last;
+ *   - Fr inputs must be canonical Montgomery limbs (value < r), as ark_bn254::Fr always is; the host-driver entry points
+ *     that take field elements (lg_circuit_constant, the var_vals of lg_prove / lg_circuit_evaluate / witness layout) return
+ *     LG_ERR_INVALID otherwise; the bulk device entry points (lg_commit & co.) do not scan their input;
  *   - only the `LigeroMTTestParams` instantiation is implemented (Blake2s-256 column hash over
  *     canonical bytes, identity leaf hash, SHA-256 two-to-one: src/ligero/types.rs:15-46).
  */

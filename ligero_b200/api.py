@@ -311,12 +311,18 @@ class LigeroCircuit:
         m, k, n, t, s = c_size_t(), c_size_t(), c_size_t(), c_size_t(), c_size_t()
         self.lib.lg_ligero_params(h, byref(m), byref(k), byref(n), byref(t), byref(s))
         self.m, self.k, self.n, self.t, self.sol_len = m.value, k.value, n.value, t.value, s.value
+        ctx._adopt(self)
+
+    def free(self):
+        """lg_ligero_free; a no-op once the context is closed (Context.close frees its circuits first)"""
+        if getattr(self, "handle", None):
+            if self.ctx.handle:
+                self.lib.lg_ligero_free(self.handle)
+            self.handle = None
 
     def __del__(self):
         try:
-            if self.handle:
-                self.lib.lg_ligero_free(self.handle)
-                self.handle = None
+            self.free()
         except Exception:
             pass
 

@@ -5,6 +5,7 @@ Everything numeric happens in libligero_b200.so on the GPU; this module only mar
 from __future__ import annotations
 
 import ctypes
+import weakref
 from ctypes import byref, c_double, c_size_t, c_void_p
 from typing import Iterable, List, Optional, Sequence
 
@@ -68,9 +69,21 @@ class Context:
                 "(ligero_b200 has no CPU fallback)")
         self.handle = h
         self.device = device
+        # objects that hold device memory of this context (committed matrices, constraint matrices, LigeroCircuits, shards):
+        # close() frees them BEFORE the context, and their own finalizers do nothing once the context is gone -- the native
+        # free functions dereference the context (include/ligero_b200.h: a context outlives everything created from it)
+        self._children = weakref.WeakSet()
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def close(self):
         if getattr(self, "handle", None):
+            for child in list(self._children):
+                try:
+                    child.free()
+                except Exception:
+                    pass
             self.lib.lg_ctx_destroy(self.handle)
             self.handle = None
 
@@ -186,10 +199,12 @@ class Constraints:
                                             len(ri), _ptr(ct) if len(ct) else None, len(ct), byref(h)),
               ctx.handle, "lg_constraints_create")
         self.handle = h
+        ctx._adopt(self)
 
     def free(self):
         if self.handle:
-            self.ctx.lib.lg_constraints_free(self.handle)
+            if self.ctx.handle:                      # the context is still alive (see Context.close)
+                self.ctx.lib.lg_constraints_free(self.handle)
             self.handle = None
 
     def __del__(self):
@@ -213,10 +228,12 @@ class CommittedMatrix:
         r, k, n = c_size_t(), c_size_t(), c_size_t()
         check(ctx.lib.lg_matrix_dims(handle, byref(r), byref(k), byref(n)), ctx.handle)
         self.rows, self.k, self.n = r.value, k.value, n.value
+        ctx._adopt(self)
 
     def free(self):
         if self.handle:
-            self.ctx.lib.lg_matrix_free(self.handle)
+            if self.ctx.handle:                      # the context is still alive (see Context.close)
+                self.ctx.lib.lg_matrix_free(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -228,6 +228,13 @@ void constant_value_ids(const lg_circuit& c, std::vector<uint32_t>& vidp, std::v
     }
 }
 
+// ark_bn254::Fr is always canonical; a C caller's limbs might not be: every value must be < r
+bool limbs_canonical(const uint64_t* vals, size_t count) {
+  for (size_t i = 0; i < count; i++)
+    if (lgh::geq_p(vals + 4 * i)) return false;
+  return true;
+}
+
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 bool debug_timing() {
   const char* e = getenv("LG_DEBUG_TIMING");
@@ -553,6 +560,20 @@ struct DevMem {
   }
 };
 
+// the verifier's R_A columns, tile by tile: planes of `nr` encoded rows (Montgomery form, plane stride nr*k) -> out[q][row0 + i]
+__global__ void gather_tile_columns_kernel(const Fr* __restrict__ planes, size_t nr, int log_k, int rho, const uint64_t* __restrict__ idx,
+                                           size_t t, size_t row0, size_t rows_total, Fr* __restrict__ out) {
+  const size_t k = (size_t)1 << log_k, tot = t * nr;
+  for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < tot; f += (size_t)gridDim.x * blockDim.x) {
+    const size_t q = f / nr, i = f % nr;
+    const size_t j = idx[q], s = j % rho, c = j / rho;
+    const uint4* src = reinterpret_cast<const uint4*>(planes + s * nr * k + i * k + c);
+    uint4* dst = reinterpret_cast<uint4*>(out + q * rows_total + row0 + i);
+    dst[0] = src[0];
+    dst[1] = src[1];
+  }
+}
+
 // cols_keep (optional): receives the device copy of the t opened columns (t x rows, contiguous) for the per-column checks
 int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::PoseidonSponge& sponge, bool* ok,
                     DevMem* cols_keep = nullptr) {
@@ -570,10 +591,16 @@ int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::Pose
     std::copy(o.columns[q].begin(), o.columns[q].end(), flat.begin() + q * rows);
   }
   Ctx* c = &L->ctx->c;
-  Fr* dcols;
-  uint8_t* ddig;
+  Fr* dcols = nullptr;
+  uint8_t* ddig = nullptr;
   LG_CUDA(c, cudaMalloc(&dcols, flat.size() * sizeof(Fr)));
-  LG_CUDA(c, cudaMalloc(&ddig, L->t * 32));
+  {
+    cudaError_t ea = cudaMalloc(&ddig, L->t * 32);
+    if (ea != cudaSuccess) {  // (do not leak the column buffer when the second allocation fails)
+      cudaFree(dcols);
+      return set_error(c, ERR_NOMEM, std::string("verify_openings cudaMalloc: ") + cudaGetErrorString(ea));
+    }
+  }
   std::vector<uint8_t> dig(L->t * 32);
   cudaMemcpyAsync(dcols, flat.data(), flat.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream);
   int s = hash_column_list(c, dcols, rows, L->t, ddig, L->ctx->col_len_prefix);
@@ -740,6 +767,10 @@ const char* lg_circuit_last_error(const lg_circuit* c) { return c ? c->error.c_s
 
 static int lg_circuit_constant_impl(lg_circuit* c, const uint64_t value[4], size_t* index_out) {  // mod.rs:76-84
   if (!c || !value) return ERR_INVALID;
+  if (lgh::geq_p(value)) {
+    c->error = "constant is not a canonical Montgomery representative (limbs >= r)";
+    return ERR_INVALID;
+  }
   Fq v;
   memcpy(v.l, value, 32);
   auto it = c->constants.find(v);
@@ -823,6 +854,7 @@ int lg_circuit_node(const lg_circuit* c, size_t index, int* type, size_t* left, 
 static int lg_circuit_evaluate_impl(const lg_circuit* c, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, const size_t* outputs,
                         size_t n_outputs, uint64_t* out_vals, size_t* n_values_out) {
   if (!c || (n_vars && (!var_idx || !var_vals)) || !outputs || !out_vals) return ERR_INVALID;
+  if (!limbs_canonical(var_vals, n_vars)) return ERR_INVALID;
   std::vector<std::pair<size_t, Fq>> vars(n_vars);
   for (size_t i = 0; i < n_vars; i++) {
     vars[i].first = var_idx[i];
@@ -1314,6 +1346,7 @@ int lg_ligero_trace_info(const lg_ligero* L, size_t* gates, size_t* levels, size
 static int lg_ligero_witness_matrix_dev_impl(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump,
                                  uint64_t* out_dev) {
   if (!L || !out_dev || (n_vars && (!var_idx || !var_vals))) return ERR_INVALID;
+  if (!limbs_canonical(var_vals, n_vars)) return fail(L->ctx, ERR_INVALID, "variable values must be canonical Montgomery limbs (< r)");
   if (!lg::is_device_ptr(out_dev)) return fail(L->ctx, ERR_INVALID, "lg_ligero_witness_matrix_dev needs a device buffer");
   const lg_circuit& c = L->circuit;
   const size_t N = c.nodes.size();
@@ -1377,6 +1410,7 @@ int lg_ligero_params(const lg_ligero* L, size_t* m, size_t* k, size_t* n, size_t
 // the pre-encoding matrix [X;Y;Z;W] (mod.rs:476-516); out: Fr[4*m*k] host
 static int lg_ligero_witness_matrix_impl(lg_ligero* L, const size_t* var_idx, const uint64_t* var_vals, size_t n_vars, int bump, uint64_t* out) {
   if (!L || !out || (n_vars && (!var_idx || !var_vals))) return ERR_INVALID;
+  if (!limbs_canonical(var_vals, n_vars)) return fail(L->ctx, ERR_INVALID, "variable values must be canonical Montgomery limbs (< r)");
   const lg_circuit& c = L->circuit;
   std::vector<std::pair<size_t, Fq>> vars(n_vars);
   for (size_t i = 0; i < n_vars; i++) {
@@ -1611,21 +1645,42 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
   }
   // ---- verify_linear (749-830)
   seed = sp.squeeze_bytes(32);
-  lg_matrix* RA = nullptr;  // r_polys evaluated on the whole large domain (816-819), resident on the device
+  // r_polys on the large domain (816-819).  The reference encodes all 4m rows of r_a at the full rate and then reads t
+  // columns.  Same values here, but the rows are encoded in tiles of at most 1024 once the opened indices are known, and
+  // the t columns of each tile are gathered right away: a 2 GiB tile at 2^24 gates instead of a 32 GiB matrix allocated
+  // next to the prover's resident one.  Only r_a itself (4mk elements) stays resident in between.
+  DevMem ra_dev;
+  LG_TRY(ra_dev.alloc(c, 4 * m * k * sizeof(Fr)));
   {
-    Fr* ra;
-    LG_CUDA(c, cudaMalloc(&ra, 4 * m * k * sizeof(Fr)));
-    int s = expand_fr(c, seed.data(), 4 * m * k, ra);
-    if (s == OK) s = lg_sparse_row_mul(ctx, L->a, (const uint64_t*)ra, (uint64_t*)ra);
-    if (s == OK) s = lg_encode(ctx, (const uint64_t*)ra, rows, k, 8, &RA);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(ra);
+    int s = expand_fr(c, seed.data(), 4 * m * k, (Fr*)ra_dev.p);
+    if (s == OK) s = lg_sparse_row_mul(ctx, L->a, (const uint64_t*)ra_dev.p, (uint64_t*)ra_dev.p);
     if (s != OK) return s;
-    vlap("r_a + full-rate encode");
+    vlap("r_a");
   }
   auto free_ra = [&]() {
-    if (RA) lg_matrix_free(RA);
-    RA = nullptr;
+    if (ra_dev.p) {
+      cudaStreamSynchronize(c->stream);
+      cudaFree(ra_dev.p);
+      ra_dev.p = nullptr;
+    }
+  };
+  // columns idx of R_A (t x rows, Montgomery) from row tiles of r_a
+  auto gather_ra_columns = [&](const uint64_t* idx_dev, Fr* out) -> int {
+    const size_t tile = rows < 1024 ? rows : 1024;
+    DevMem planes;
+    LG_TRY(planes.alloc(c, 8 * tile * k * sizeof(Fr)));
+    int log_k = 0;
+    while (((size_t)1 << log_k) < k) log_k++;
+    for (size_t row0 = 0; row0 < rows; row0 += tile) {
+      const size_t nr = row0 + tile <= rows ? tile : rows - row0;
+      Fr* p0 = (Fr*)planes.p;
+      LG_TRY(lg::encode_rows(c, (const Fr*)ra_dev.p + row0 * k, nr, log_k, 8, p0, p0 + nr * k, nullptr, false));
+      gather_tile_columns_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(p0, nr, log_k, 8, idx_dev, L->t, row0, rows, out);
+      c->launches++;
+      LG_CUDA(c, cudaGetLastError());
+    }
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OK;
   };
   const std::vector<Fq>& ql = P->linear_poly;
   const size_t deg_l = ql.empty() ? 0 : ql.size() - 1;
@@ -1659,11 +1714,11 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
     if (s == OK && cudaMemcpyAsync(idx_dev.p, P->linear.leaf_index.data(), L->t * sizeof(uint64_t), cudaMemcpyHostToDevice,
                                    c->stream) != cudaSuccess)
       s = fail(ctx, ERR_CUDA, "index upload failed");
-    if (s == OK) s = lg::gather_open(c, RA->m, (const uint64_t*)idx_dev.p, L->t, (Fr*)rcols.p, nullptr, nullptr);
+    if (s == OK) s = gather_ra_columns((const uint64_t*)idx_dev.p, (Fr*)rcols.p);
+    vlap("R_A row tiles: encode + gather");
     if (s == OK) s = run_checks(1, cols, rcols.p);
-    vlap("openings + checks (linear)");
+    vlap("checks (linear)");
     free_ra();
-    vlap("free R_A");
     if (s != OK) return s;
     std::vector<Fq> q_n;
     LG_TRY(on_large_domain(ie, q_n));

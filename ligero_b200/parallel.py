@@ -183,6 +183,10 @@ class ShardedCommitter:
         self.mat_cols = CommittedMatrix(ctx, ctx.lib.lg_shard_matrix(self.handle), None)
         self.mat_cols.free = lambda: None            # borrowed: owned by the shard
         self.subtree_roots = None
+        ctx._adopt(self)
+
+    def free(self):
+        self.close()
 
     def set_pipeline(self, enabled):
         """0 / False: off; 1 / True: eager (hash beside the next block's shared-memory kernel); 2: deferred (hash beside the
@@ -192,7 +196,7 @@ class ShardedCommitter:
         check(self.ctx.lib.lg_shard_set_pipeline(self.handle, v), self.ctx.handle, "lg_shard_set_pipeline")
 
     def close(self):
-        if getattr(self, "handle", None):
+        if getattr(self, "handle", None) and self.ctx.handle:
             self.ctx.sync()
             if self.world > 1:
                 dist.barrier()                           # nobody unmaps a shard a peer may still be writing

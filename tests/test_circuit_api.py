@@ -198,3 +198,33 @@ def test_from_constraint_system_equals_the_oracle():
     assert circ.num_nodes() == 15
     with pytest.raises(lb.LigeroB200Error):                      # an empty row: add_nodes(empty).unwrap() panics (148-153)
         lb.ArithmeticCircuit.from_constraint_system([[]], [[(1, 1)]], [[(1, 1)]], 2)
+
+
+def test_non_canonical_limbs_are_refused_at_the_abi():
+    """ADVICE r1: raw Montgomery limbs >= r from a C caller (ark_bn254::Fr can never hold them) are LG_ERR_INVALID, not a
+    silently different circuit: a non-canonical 1 would miss the constant table and shift the witness layout."""
+    import numpy as np
+    from ctypes import byref, c_size_t
+    from ligero_b200 import _lib
+    from ligero_b200.backend import _ptr, fr_to_limbs
+    import ligero_b200 as lb
+    lib = _lib.load()
+    c = lb.ArithmeticCircuit()
+    r_limbs = np.array([[0x43e1f593f0000001, 0x2833e84879b97091, 0xb85045b68181585d, 0x30644e72e131a029]], dtype=np.uint64)
+    carry = 0                                                                    # the Montgomery 1 shifted by r: same residue
+    vals = []
+    for a, b in zip(fr_to_limbs([1])[0].tolist(), r_limbs[0].tolist()):
+        t = a + b + carry
+        vals.append(t & (2 ** 64 - 1))
+        carry = t >> 64
+    bad = np.array([vals], dtype=np.uint64)
+    idx = c_size_t()
+    assert lib.lg_circuit_constant(c.handle, _ptr(bad), byref(idx)) == 1          # LG_ERR_INVALID
+    assert lib.lg_circuit_constant(c.handle, _ptr(fr_to_limbs([1])), byref(idx)) == 0
+    x = c.new_variable()
+    out = c.add(x, idx.value)
+    var_idx = np.array([x], dtype=np.uint64)
+    outs = np.array([out], dtype=np.uint64)
+    res = np.zeros((1, 4), dtype=np.uint64)
+    assert lib.lg_circuit_evaluate(c.handle, _ptr(var_idx), _ptr(bad), 1, _ptr(outs), 1, _ptr(res), None) == 1
+    assert lib.lg_circuit_evaluate(c.handle, _ptr(var_idx), _ptr(fr_to_limbs([5])), 1, _ptr(outs), 1, _ptr(res), None) == 0

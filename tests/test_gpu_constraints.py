@@ -49,9 +49,14 @@ def test_device_csc_with_circuit_constants_and_many_outputs(gpu_ctx, monkeypatch
     mk = olc.m * olc.k
     ocp, ori, ovi, otab = csc_right_block(olc.a, mk)
     col_ptr, row_idx, val_id, table = r["1"][1]
-    assert np.array_equal(col_ptr, ocp) and np.array_equal(row_idx, ori)
+    assert np.array_equal(col_ptr, ocp)
 
     def values(vid, tab):
         t = lb.limbs_to_fr(tab) if tab is not None and len(tab) else []
         return [1 if v == 0 else P - 1 if v == 1 else t[v - 2] for v in vid.tolist()]
-    assert values(val_id, table) == values(ovi, otab)
+
+    def by_column(cp, ri, vals):
+        # the product keeps the reference's generation order inside a column (gate by gate), the oracle helper lists a
+        # column by ascending row: compare the (row, value) sets
+        return [sorted(zip(ri[cp[j]:cp[j + 1]].tolist(), vals[cp[j]:cp[j + 1]])) for j in range(len(cp) - 1)]
+    assert by_column(col_ptr, row_idx, values(val_id, table)) == by_column(ocp, ori, values(ovi, otab))
