@@ -509,6 +509,11 @@ int lg_ctx_destroy(lg_ctx* ctx) {
     }
     cudaStreamDestroy(ctx->c.copy_stream);
   }
+  if (ctx->c.open_stream) {
+    cudaStreamSynchronize(ctx->c.open_stream);
+    cudaStreamDestroy(ctx->c.open_stream);
+    cudaEventDestroy(ctx->c.ev_gathered);
+  }
   if (ctx->c.hash_stream_hi) {
     cudaStreamSynchronize(ctx->c.hash_stream_hi);
     cudaStreamDestroy(ctx->c.hash_stream_hi);

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -33,11 +34,106 @@ struct Node {
 
 typedef std::array<uint8_t, 32> Digest;
 
+// pinned host buffers for opened columns, recycled across proofs (cudaHostAlloc of 82 MB costs more than the copy it serves)
+struct PinnedPool {
+  std::mutex mu;
+  std::multimap<size_t, void*> idle;
+  void* get(size_t bytes, size_t* got) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = idle.lower_bound(bytes);
+      if (it != idle.end() && it->first <= 2 * bytes + 4096) {
+        void* p = it->second;
+        *got = it->first;
+        idle.erase(it);
+        return p;
+      }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    *got = bytes;
+    return p;
+  }
+  void put(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> g(mu);
+    size_t held = 0;
+    for (auto& kv : idle) held += kv.first;
+    if (held + bytes > ((size_t)1 << 30)) {  // keep at most 1 GiB idle
+      cudaFreeHost(p);
+      return;
+    }
+    idle.emplace(bytes, p);
+  }
+};
+PinnedPool& pinned_pool() {
+  static PinnedPool* pool = new PinnedPool();  // leaked on purpose: the CUDA runtime may be gone at static destruction
+  return *pool;
+}
+
+// t opened columns of `rows` elements each, stored column after column in ONE buffer: the prover's buffer comes from the
+// pinned pool and the device-to-host copy of an opening lands in it directly (no staging copy, no per-column vectors: 82 MB
+// per opening at 2^24 gates); a deserialised proof owns a vector.  Columns of unequal length (malformed proofs) are kept
+// apart so that they serialise back unchanged and never verify.
 struct Opened {
-  std::vector<std::vector<Fq>> columns;
+  Fq* cols = nullptr;
+  size_t t = 0, rows = 0;
+  size_t pinned_bytes = 0;  // > 0: cols belongs to the pinned pool
+  std::vector<Fq> own;
+  std::vector<std::vector<Fq>> ragged;
+  bool is_ragged = false;
   std::vector<uint64_t> leaf_index;
   std::vector<Digest> sibling;
   std::vector<std::vector<Digest>> auth;
+
+  Opened() = default;
+  Opened(const Opened&) = delete;
+  Opened& operator=(const Opened&) = delete;
+  Opened(Opened&& o) noexcept { *this = std::move(o); }
+  Opened& operator=(Opened&& o) noexcept {
+    if (this == &o) return *this;
+    release();
+    const bool was_own = o.pinned_bytes == 0 && o.cols != nullptr;
+    own = std::move(o.own);
+    cols = was_own ? own.data() : o.cols;
+    t = o.t;
+    rows = o.rows;
+    pinned_bytes = o.pinned_bytes;
+    ragged = std::move(o.ragged);
+    is_ragged = o.is_ragged;
+    leaf_index = std::move(o.leaf_index);
+    sibling = std::move(o.sibling);
+    auth = std::move(o.auth);
+    o.cols = nullptr;
+    o.pinned_bytes = 0;
+    o.t = o.rows = 0;
+    return *this;
+  }
+  ~Opened() { release(); }
+  void release() {
+    if (pinned_bytes) pinned_pool().put(cols, pinned_bytes);
+    cols = nullptr;
+    pinned_bytes = 0;
+  }
+  // false: out of (pinned) memory
+  bool alloc(size_t t_, size_t rows_, bool pinned) {
+    release();
+    t = t_;
+    rows = rows_;
+    is_ragged = false;
+    if (pinned && t * rows) {
+      cols = (Fq*)pinned_pool().get(t * rows * sizeof(Fq), &pinned_bytes);
+      if (cols) return true;
+      pinned_bytes = 0;
+    }
+    own.assign(t * rows, lgh::kZero);
+    cols = own.data();
+    return true;
+  }
+  const Fq* col(size_t q) const { return cols + q * rows; }
+  size_t n_columns() const { return is_ragged ? ragged.size() : t; }
 };
 
 }  // namespace
@@ -493,22 +589,48 @@ int open_columns(lg_ligero* L, lg_matrix* U, lgh::PoseidonSponge& sponge, Opened
   const std::vector<uint8_t> seed = sponge.squeeze_bytes(32);
   std::vector<uint64_t> idx(L->t);
   LG_TRY(lg_expand_indices(seed.data(), L->n, L->t, idx.data()));
-  const size_t rows = 4 * L->m;
+  const size_t rows = 4 * L->m, t = L->t;
   int log_n = 0;
   while (((size_t)1 << log_n) < L->n) log_n++;
   const size_t depth = (size_t)(log_n - 1);
-  // t x R elements (82 MB at 2^24 gates): device -> pinned staging at full PCIe rate, then one pass into the proof
-  void* stage = nullptr;
-  LG_TRY(lg::ctx_host_stage(&L->ctx->c, L->t * rows * sizeof(Fq), &stage));
-  const Fq* cols = (const Fq*)stage;
-  std::vector<uint8_t> sib(L->t * 32), auth(L->t * depth * 32 + 1);
-  LG_TRY(lg_open(U, idx.data(), L->t, (uint64_t*)stage, sib.data(), auth.data()));
-  out.columns.resize(L->t);
+  Ctx* c = &L->ctx->c;
+  cudaSetDevice(c->device);
+  for (size_t q = 0; q < t; q++)
+    if (idx[q] >= U->m.n) return fail(L->ctx, ERR_INVALID, "column index out of range");
+  // The t x R elements (82 MB at 2^24 gates) go device -> pinned proof buffer on their own stream: nothing the
+  // transcript does next depends on them (the openings are not absorbed), so the copy runs behind the next test and
+  // lg_prove_matrix waits for it once, at the end.
+  if (!c->open_stream) {
+    LG_CUDA(c, cudaStreamCreateWithFlags(&c->open_stream, cudaStreamNonBlocking));
+    LG_CUDA(c, cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming));
+  }
+  out.alloc(t, rows, true);
+  uint64_t* d_idx = nullptr;
+  Fr* d_cols = nullptr;
+  uint8_t *d_sib = nullptr, *d_auth = nullptr;
+  LG_CUDA(c, cudaMallocAsync((void**)&d_idx, t * 8, c->stream));
+  LG_CUDA(c, cudaMallocAsync((void**)&d_cols, t * rows * sizeof(Fr), c->stream));
+  LG_CUDA(c, cudaMallocAsync((void**)&d_sib, t * 32, c->stream));
+  LG_CUDA(c, cudaMallocAsync((void**)&d_auth, t * depth * 32 + 32, c->stream));
+  LG_CUDA(c, cudaMemcpyAsync(d_idx, idx.data(), t * 8, cudaMemcpyHostToDevice, c->stream));
+  lg::phase_mark(c, lg::PH_BEGIN);
+  LG_TRY(lg::gather_open(c, U->m, d_idx, t, d_cols, d_sib, d_auth));
+  lg::phase_mark(c, lg::PH_OPEN);
+  LG_CUDA(c, cudaEventRecord(c->ev_gathered, c->stream));
+  LG_CUDA(c, cudaStreamWaitEvent(c->open_stream, c->ev_gathered, 0));
+  LG_CUDA(c, cudaMemcpyAsync(out.cols, d_cols, t * rows * sizeof(Fr), cudaMemcpyDeviceToHost, c->open_stream));
+  LG_CUDA(c, cudaFreeAsync(d_cols, c->open_stream));  // released when the copy is done
+  std::vector<uint8_t> sib(t * 32), auth(t * depth * 32 + 1);
+  LG_CUDA(c, cudaMemcpyAsync(sib.data(), d_sib, t * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (depth) LG_CUDA(c, cudaMemcpyAsync(auth.data(), d_auth, t * depth * 32, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaFreeAsync(d_idx, c->stream));
+  LG_CUDA(c, cudaFreeAsync(d_sib, c->stream));
+  LG_CUDA(c, cudaFreeAsync(d_auth, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
   out.leaf_index = idx;
-  out.sibling.resize(L->t);
-  out.auth.assign(L->t, std::vector<Digest>(depth));
-  for (size_t q = 0; q < L->t; q++) {
-    out.columns[q].assign(cols + q * rows, cols + (q + 1) * rows);
+  out.sibling.resize(t);
+  out.auth.assign(t, std::vector<Digest>(depth));
+  for (size_t q = 0; q < t; q++) {
     memcpy(out.sibling[q].data(), sib.data() + 32 * q, 32);
     for (size_t d = 0; d < depth; d++) memcpy(out.auth[q][d].data(), auth.data() + 32 * (q * depth + d), 32);
   }
@@ -582,18 +704,17 @@ int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::Pose
   std::vector<uint64_t> idx(L->t);
   LG_TRY(lg_expand_indices(seed.data(), L->n, L->t, idx.data()));
   const size_t rows = 4 * L->m;
-  if (o.columns.size() != L->t || o.leaf_index.size() != L->t || o.sibling.size() != L->t || o.auth.size() != L->t) return OK;
+  if (o.is_ragged || o.t != L->t || o.rows != rows || o.leaf_index.size() != L->t || o.sibling.size() != L->t || o.auth.size() != L->t)
+    return OK;
   int log_n = 0;
   while (((size_t)1 << log_n) < L->n) log_n++;
-  std::vector<Fq> flat(L->t * rows);
-  for (size_t q = 0; q < L->t; q++) {
-    if (o.columns[q].size() != rows || o.auth[q].size() != (size_t)(log_n - 1)) return OK;
-    std::copy(o.columns[q].begin(), o.columns[q].end(), flat.begin() + q * rows);
-  }
+  for (size_t q = 0; q < L->t; q++)
+    if (o.auth[q].size() != (size_t)(log_n - 1)) return OK;
+  const size_t flat_elems = L->t * rows;
   Ctx* c = &L->ctx->c;
   Fr* dcols = nullptr;
   uint8_t* ddig = nullptr;
-  LG_CUDA(c, cudaMalloc(&dcols, flat.size() * sizeof(Fr)));
+  LG_CUDA(c, cudaMalloc(&dcols, flat_elems * sizeof(Fr)));
   {
     cudaError_t ea = cudaMalloc(&ddig, L->t * 32);
     if (ea != cudaSuccess) {  // (do not leak the column buffer when the second allocation fails)
@@ -602,7 +723,7 @@ int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::Pose
     }
   }
   std::vector<uint8_t> dig(L->t * 32);
-  cudaMemcpyAsync(dcols, flat.data(), flat.size() * sizeof(Fr), cudaMemcpyHostToDevice, c->stream);
+  cudaMemcpyAsync(dcols, o.cols, flat_elems * sizeof(Fr), cudaMemcpyHostToDevice, c->stream);
   int s = hash_column_list(c, dcols, rows, L->t, ddig, L->ctx->col_len_prefix);
   cudaMemcpyAsync(dig.data(), ddig, dig.size(), cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
@@ -657,9 +778,20 @@ struct Writer {
     u64(32);
     raw(d.data(), 32);
   }
+  void frs(const Fq* v, size_t n) {
+    u64(n);
+    if (!p) {
+      pos += 32 * n;
+      return;
+    }
+    for (size_t i = 0; i < n; i++) fr(v[i]);
+  }
   void opened(const Opened& o) {
-    u64(o.columns.size());
-    for (auto& col : o.columns) frs(col);
+    u64(o.n_columns());
+    if (o.is_ragged)
+      for (auto& col : o.ragged) frs(col);
+    else
+      for (size_t q = 0; q < o.t; q++) frs(o.col(q), o.rows);
     u64(o.leaf_index.size());
     for (size_t q = 0; q < o.leaf_index.size(); q++) {  // Path { leaf_sibling_hash, auth_path, leaf_index }
       digest(o.sibling[q]);
@@ -725,7 +857,17 @@ struct Reader {
       ok = false;
       return o;
     }
-    for (uint64_t i = 0; i < nc && ok; i++) o.columns.push_back(frs());
+    std::vector<std::vector<Fq>> colv;
+    for (uint64_t i = 0; i < nc && ok; i++) colv.push_back(frs());
+    bool same = true;
+    for (auto& cv : colv) same = same && cv.size() == colv[0].size();
+    if (same) {
+      o.alloc(colv.size(), colv.empty() ? 0 : colv[0].size(), false);
+      for (size_t q = 0; q < colv.size(); q++) std::copy(colv[q].begin(), colv[q].end(), o.cols + q * o.rows);
+    } else {
+      o.is_ragged = true;
+      o.ragged = std::move(colv);
+    }
     uint64_t np = u64();
     if (!ok || np > len) {
       ok = false;
@@ -1476,6 +1618,11 @@ static int lg_prove_matrix_impl(lg_ligero* L, const uint64_t* preenc_u, lg_spong
     if (s == OK) L->u_cache = U;
   }
   auto done = [&](int code) {
+    // the three openings' device-to-host copies run on their own stream (open_columns): wait for them before the proof
+    // (or its buffers) leaves this call
+    lg::Ctx* cx = &ctx->c;
+    if (cx->open_stream && cudaStreamSynchronize(cx->open_stream) != cudaSuccess && code == OK)
+      code = fail(ctx, ERR_CUDA, "opened-column copy failed");
     if (code != OK) {
       delete P;
     } else {
@@ -1789,13 +1936,12 @@ static int lg_proof_assemble_impl(const uint8_t root[32], const uint64_t* preenc
       return ERR_INVALID;
     }
     Opened& o = *parts[p];
-    o.columns.resize(t);
+    o.alloc(t, rows, false);
+    if (t * rows) memcpy(o.cols, cols[p], t * rows * 32);
     o.leaf_index.assign(idx[p], idx[p] + t);
     o.sibling.resize(t);
     o.auth.assign(t, std::vector<Digest>(depth));
     for (size_t q = 0; q < t; q++) {
-      o.columns[q].resize(rows);
-      memcpy(o.columns[q].data(), cols[p] + 4 * q * rows, rows * 32);
       memcpy(o.sibling[q].data(), sib[p] + 32 * q, 32);
       for (size_t d = 0; d < depth; d++) memcpy(o.auth[q][d].data(), auth[p] + 32 * (q * depth + d), 32);
     }

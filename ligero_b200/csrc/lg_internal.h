@@ -108,6 +108,9 @@ struct Ctx {
   // column hashes (whole or row tiles) of at most this many columns use the four-lanes-per-column kernel (hash.cu);
   // lg_ctx_set_hash_quad_max / LG_HASH_QUAD_MAX override, 0 disables
   size_t hash_quad_max = 8192;
+  // the prover's opened columns go device -> pinned proof buffer on this stream, behind the next test (capi_host.cu)
+  cudaStream_t open_stream = nullptr;
+  cudaEvent_t ev_gathered = nullptr;
   // pinned host staging for large device-to-host results (opened columns), grown on demand
   void* host_stage = nullptr;
   size_t host_stage_bytes = 0;
