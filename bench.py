@@ -410,6 +410,7 @@ def main():
         wmsg = msg.clone().view(4, m, k, 4)
         wmsg[:, data_rows:] = 0
         wmsg = wmsg.view(R * k, 4)
+        torch.cuda.synchronize()             # torch's stream wrote wmsg; the library reads it on its own stream
         for _ in range(2):
             check(ctx.lib.lg_recommit(cm.handle, _ptr(wmsg), None), ctx.handle, "lg_recommit")
         torch.cuda.synchronize()
@@ -430,6 +431,7 @@ def main():
     if not args.no_e2e:
         host = torch.empty((R * k, 4), dtype=torch.int64, pin_memory=True)
         host.copy_(msg)
+        torch.cuda.synchronize()
         root_host = np.zeros(32, dtype=np.uint8)
         for _ in range(2):
             check(ctx.lib.lg_recommit(cm.handle, _ptr(host), _ptr(root_host)), ctx.handle, "lg_recommit(host)")

@@ -236,6 +236,7 @@ class ShardedCommitter:
         sc = ShardedCommitter(ctx, m, k, rho, rank, world, pipeline, sub)
         dev = sc.dev
         msg = matrix_rows_torch(seed, sc.row_ids, k, dev) if sc.rows_g else torch.zeros((k, 4), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()             # the library's stream does not wait for torch's
         for _ in range(args.warmup):
             sc.commit_async(msg)
         root0 = sc.root()
@@ -275,6 +276,7 @@ class ShardedCommitter:
                     "e2e": None, "root": root0.hex(), "kernel_ms_rank0": kernel_ms, "gpu_launches": int(launches)}
         host = torch.empty_like(msg, device="cpu").pin_memory()
         host.copy_(msg)
+        torch.cuda.synchronize()
         if pipeline is None and "LG_SHARD_PIPELINE" not in os.environ:
             sc.set_pipeline(int(os.environ.get("LG_MGPU_E2E_PIPELINE", "1")))   # host input: the upload paces the encoder
         sc.commit(host)
@@ -333,7 +335,9 @@ class ShardedProver:
         """this rank's rows (lg_shard_layout order) of a full 4m x k pre-encoding matrix (numpy or torch, [4mk, 4])"""
         full = torch.as_tensor(preenc_u.view("int64") if hasattr(preenc_u, "ctypes") else preenc_u)
         loc = full.view(self.rows, self.k, 4)[self.row_ids.to(full.device)].reshape(-1, 4).contiguous()
-        return loc.to(self.committer.dev)
+        loc = loc.to(self.committer.dev)
+        torch.cuda.synchronize(self.committer.dev)   # torch's stream produced it; the library reads it on its own
+        return loc
 
     def prove(self, var_assignment, sponge):
         import numpy as np

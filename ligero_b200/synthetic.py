@@ -69,4 +69,7 @@ def matrix_rows_torch(seed: int, row_ids, k: int, device, chunk_rows: int = 1024
         z = z ^ lsr(z, 31)
         z[:, :, 3] = lsr(z[:, :, 3], 1) % R_TOP
         out[r0 * k:(r0 + rows.shape[0]) * k] = z.reshape(-1, 4)
+    if out.is_cuda:
+        # the library launches on its own non-blocking stream, which does not wait for torch's: hand over a finished matrix
+        torch.cuda.synchronize(out.device)
     return out

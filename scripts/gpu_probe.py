@@ -15,6 +15,7 @@ for (R, k, rho) in shapes:
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     msg = torch.randint(0, 2**62, (R * k, 4), dtype=torch.int64, device="cuda", generator=g)
     msg[:, 3] &= (1 << 60) - 1
+    torch.cuda.synchronize()
     cm = ctx.commit(msg, R, k, rho)
     for rep in range(3):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]

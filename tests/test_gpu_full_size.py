@@ -23,6 +23,7 @@ def full(gpu_ctx):
     msg = torch.randint(0, 2 ** 62, (R * K, 4), dtype=torch.int64, device="cuda", generator=g)
     msg[:, 3] &= (1 << 60) - 1
     msg.view(R, K, 4)[R // 3] = 0                       # one all-zero row (short-circuited by the encoder)
+    torch.cuda.synchronize()                            # the library's stream does not wait for torch's
     cm = gpu_ctx.commit(msg, R, K, RHO)
     yield gpu_ctx, msg, cm
     cm.free()
