@@ -367,12 +367,12 @@ static int encode_sharded_tiled(lg_ctx* ctx, const uint64_t* src, size_t rows, i
     LG_CUDA(c, cudaMalloc(&c->tile_cosets, cos_bytes));
     c->tile_cosets_bytes = cos_bytes;
   }
-  LG_CUDA(c, cudaEventRecord(c->ev_consumed[0], c->stream));
-  LG_CUDA(c, cudaEventRecord(c->ev_consumed[1], c->stream));
-  int t = 0;
-  for (size_t row0 = 0; row0 < rows; row0 += tile_rows, t++) {
+  // The two staging tiles alternate ACROSS calls (Ctx::stage_seq): the multi-GPU committer encodes its rows run by run,
+  // one call per run, and the upload of run j+1 must overlap the encoding of run j.  A tile is overwritten only after the
+  // encode that read it (ev_consumed, recorded after every use here and in encode_tiled).
+  for (size_t row0 = 0; row0 < rows; row0 += tile_rows) {
     const size_t nr = row0 + tile_rows <= rows ? tile_rows : rows - row0;
-    const int b = t & 1;
+    const int b = (int)(c->stage_seq++ & 1);
     LG_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
     LG_CUDA(c, cudaMemcpyAsync(c->stage[b], (const uint8_t*)src + row0 * row_bytes, nr * row_bytes, cudaMemcpyHostToDevice,
                                c->copy_stream));
@@ -763,7 +763,10 @@ int lg_encode_sharded_rows(lg_ctx* ctx, const uint64_t* msg_rows, size_t nrows, 
   map.m = map.m_g = (uint32_t)nrows;  // one block of consecutive global rows: grow(i) = row_base + i
   map.i0 = (uint32_t)row_base;
   map.rows_total = rows_total;
-  if (!is_device_ptr(msg_rows) && nrows * k * sizeof(Fr) >= ((size_t)64 << 20) && nrows < ((size_t)1 << 31))
+  // host rows go through the staged upload (copy stream + two staging tiles, reused across calls) from 1 MiB on: the
+  // pipeline steps of the multi-GPU committer are runs of a few tens of MiB, and a cudaMalloc / cudaFree per run would
+  // serialise the device
+  if (!is_device_ptr(msg_rows) && nrows * k * sizeof(Fr) >= ((size_t)1 << 20) && nrows < ((size_t)1 << 31))
     return encode_sharded_tiled(ctx, msg_rows, nrows, log_k, (int)rho_inv, map, plain != 0);
   const Fr* dev;
   void* to_free;

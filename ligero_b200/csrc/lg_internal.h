@@ -85,6 +85,7 @@ struct Ctx {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes = 0;
+  uint64_t stage_seq = 0;  // staging tiles alternate across calls of the sharded encoder (capi.cu)
   void* tile_cosets = nullptr;
   size_t tile_cosets_bytes = 0;
   // commit pipeline: column hashing of row tile i (high-priority stream) overlaps the encoding of tile i+1
