@@ -65,3 +65,22 @@ def test_nothing_at_run_time_reads_the_reference_tree():
     assert len(files) > 30
     for p in files:
         assert "/root/reference" not in open(p).read(), f"{p} names /root/reference"
+
+
+def test_header_is_valid_c_and_the_c_host_example_links():
+    """include/ligero_b200.h compiled as C11 by gcc, and tests/c/mgpu_prove.c (a C host driving lg_mgpu_prove) linked
+    against the in-tree library; without a GPU the program stops at lg_ctx_create with LG_ERR_CUDA -- no CPU fallback."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "ligero_b200")
+    with tempfile.TemporaryDirectory() as tmp:
+        exe = os.path.join(tmp, "mgpu_prove")
+        r = subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                            os.path.join(root, "tests", "c", "mgpu_prove.c"), "-o", exe, "-L", libdir, "-lligero_b200",
+                            f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        import torch
+        if not torch.cuda.is_available():
+            run = subprocess.run([exe, "1", "6"], capture_output=True, text=True)
+            assert run.returncode != 0 and "lg_ctx_create" in run.stderr

@@ -49,3 +49,22 @@ def test_single_process_mgpu(n):
         pytest.skip(f"needs {n} GPUs")
     r = run([sys.executable, os.path.join("scripts", "mgpu_single_process_check.py"), str(n)])
     assert "MGPU_SP_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def build_c_host(tmp_path):
+    exe = str(tmp_path / "mgpu_prove")
+    libdir = os.path.join(ROOT, "ligero_b200")
+    r = run(["gcc", "-std=c11", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "mgpu_prove.c"), "-o", exe,
+             "-L", libdir, "-lligero_b200", f"-Wl,-rpath,{libdir}"])
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_c_host_drives_the_multi_gpu_prover(n, tmp_path):
+    """tests/c/mgpu_prove.c: a C program (no Python, no torch) proves over n GPUs through lg_mgpu_* and gets the single-GPU
+    proof bytes; n = 1 runs on any GPU box, n = 2 needs two."""
+    if gpu_count() < n:
+        pytest.skip(f"needs {n} GPUs")
+    r = run([build_c_host(tmp_path), str(n), "14"])
+    assert "C_MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -90,6 +90,32 @@ def test_partition_covers_every_row_once():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_sub_block_runs_cover_every_row_once_and_keep_block_order():
+    """lg_shard_layout's mirror (local_row_ids with sub-blocks): the 4 * sub pipeline steps of all ranks together cover the
+    rows of one block of global rows each, in row order -- what lets the column owner hash step j as soon as every rank has
+    delivered its j-th run (src/ligero/mod.rs:536-542: one BLAKE2s stream per column, rows in order)."""
+    for m in (1, 3, 86, 513, 4097):
+        for world in (1, 2, 8):
+            for sub in (1, 2, 3, 4):
+                if sub > m:
+                    continue
+                per_rank = [par.local_row_ids(m, world, r, sub) for r in range(world)]
+                assert sorted(i for ids in per_rank for i in ids) == list(range(4 * m))
+                # step boundaries: block b, sub-block u covers [b*m + s0, b*m + s1)
+                bounds = [(b * m + s0, b * m + s1) for b in range(4) for (s0, s1) in par.block_slices(m, sub)]
+                pos = [0] * world
+                for (lo, hi) in bounds:
+                    got = []
+                    for r in range(world):
+                        a, e = par.block_slices(hi - lo, world)[r]
+                        run = per_rank[r][pos[r]:pos[r] + (e - a)]
+                        pos[r] += e - a
+                        assert run == list(range(lo + a, lo + e))       # a run of consecutive global rows
+                        got += run
+                    assert got == list(range(lo, hi))
+                assert all(pos[r] == len(per_rank[r]) for r in range(world))
+
+
 def test_top_of_tree():
     import hashlib
     roots = [bytes([i]) * 32 for i in range(4)]
