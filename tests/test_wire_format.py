@@ -54,3 +54,26 @@ def test_malformed_bytes_are_refused():
             LigeroProof.from_bytes(bytes(t)).to_bytes()
         except LigeroB200Error:
             pass
+
+
+def test_columns_of_unequal_length_round_trip_unchanged():
+    """The product stores the t opened columns of one opening in a single flat buffer (the device-to-host copy lands in it);
+    a deserialised proof whose columns differ in length cannot use that layout -- it must still serialise back byte for byte
+    (and can never verify: lg_verify checks every column against 4m rows)."""
+    lc, proof = oracle_proof(5, 30)
+    cols = proof.interleaved.columns
+    cols[1] = cols[1][:-2]                      # one shorter column
+    cols[3] = cols[3] + [7, 8, 9]               # one longer column
+    blob = wire.serialize_proof(proof)
+    assert LigeroProof.from_bytes(blob).to_bytes() == blob
+    # all columns shorter by the same amount: the flat layout again
+    lc, proof = oracle_proof(5, 30)
+    proof.linear.columns[:] = [c[:-1] for c in proof.linear.columns]
+    blob = wire.serialize_proof(proof)
+    assert LigeroProof.from_bytes(blob).to_bytes() == blob
+    # no columns at all
+    lc, proof = oracle_proof(5, 30)
+    proof.quadratic.columns[:] = []
+    proof.quadratic.paths[:] = []
+    blob = wire.serialize_proof(proof)
+    assert LigeroProof.from_bytes(blob).to_bytes() == blob
