@@ -7,6 +7,7 @@
 //   * PoseidonSponge with arkworks' duplex rules.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -162,6 +163,51 @@ __attribute__((target("bmi2"))) inline Fq mul_mulx(const Fq& a, const Fq& b) {
 }
 inline bool cpu_has_mulx() {
   static const bool v = __builtin_cpu_supports("bmi2") != 0;
+  return v;
+}
+// Montgomery product with MULX and the two ADX carry chains (adcx: low halves, adox: high halves): CIOS, the four rounds
+// unrolled with the accumulator registers renamed instead of shifted.  LAZY: inputs < 2p, result < 2p (4p^2 < p 2^256), no final
+// subtraction.  1.4x the throughput of the compiler's code when independent products are in flight (the three S-boxes of a full
+// Poseidon round), the same latency for a dependent chain.  Used by the sponge's width-3 fast path only.
+#define LGH_HAVE_ADX 1
+__attribute__((target("bmi2,adx"))) static inline void mul_adx_lazy(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
+  uint64_t t0, t1, t2, t3, t4, lo, hi, zero;
+  static const uint64_t P[4] = {kP[0], kP[1], kP[2], kP[3]};
+  const uint64_t pinv = kPInv;
+#define LGH_ADX_ROUND(BI, T0, T1, T2, T3, T4)                                                                          \
+  "movq " BI "(%[b]), %%rdx\n\t"                                                                                        \
+  "xorq %[zero], %[zero]\n\t"                                                                                           \
+  "mulx 0(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[" T0 "]\n\t adox %[hi], %[" T1 "]\n\t"                                   \
+  "mulx 8(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[" T1 "]\n\t adox %[hi], %[" T2 "]\n\t"                                   \
+  "mulx 16(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[" T2 "]\n\t adox %[hi], %[" T3 "]\n\t"                                  \
+  "mulx 24(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[" T3 "]\n\t movq %[zero], %[" T4 "]\n\t adox %[hi], %[" T4 "]\n\t"       \
+  "adcx %[zero], %[" T4 "]\n\t"                                                                                          \
+  "movq %[" T0 "], %%rdx\n\t imulq %[pinv], %%rdx\n\t"                                                                   \
+  "xorq %[zero], %[zero]\n\t"                                                                                           \
+  "mulx 0(%[p]), %[lo], %[hi]\n\t adcx %[lo], %[" T0 "]\n\t adox %[hi], %[" T1 "]\n\t"                                   \
+  "mulx 8(%[p]), %[lo], %[hi]\n\t adcx %[lo], %[" T1 "]\n\t adox %[hi], %[" T2 "]\n\t"                                   \
+  "mulx 16(%[p]), %[lo], %[hi]\n\t adcx %[lo], %[" T2 "]\n\t adox %[hi], %[" T3 "]\n\t"                                  \
+  "mulx 24(%[p]), %[lo], %[hi]\n\t adcx %[lo], %[" T3 "]\n\t adox %[hi], %[" T4 "]\n\t"                                  \
+  "adcx %[zero], %[" T4 "]\n\t"
+  asm volatile(
+      "xorq %[t0], %[t0]\n\t xorq %[t1], %[t1]\n\t xorq %[t2], %[t2]\n\t xorq %[t3], %[t3]\n\t"
+      LGH_ADX_ROUND("0", "t0", "t1", "t2", "t3", "t4")
+      LGH_ADX_ROUND("8", "t1", "t2", "t3", "t4", "t0")
+      LGH_ADX_ROUND("16", "t2", "t3", "t4", "t0", "t1")
+      LGH_ADX_ROUND("24", "t3", "t4", "t0", "t1", "t2")
+      : [t0] "=&r"(t0), [t1] "=&r"(t1), [t2] "=&r"(t2), [t3] "=&r"(t3), [t4] "=&r"(t4), [lo] "=&r"(lo), [hi] "=&r"(hi),
+        [zero] "=&r"(zero)
+      : [a] "r"(a), [b] "r"(b), [p] "r"(P), [pinv] "r"(pinv)
+      : "rdx", "cc", "memory");
+#undef LGH_ADX_ROUND
+  // after four rounds the value sits in (t4, t0, t1, t2); t3 == 0
+  r[0] = t4;
+  r[1] = t0;
+  r[2] = t1;
+  r[3] = t2;
+}
+inline bool cpu_has_adx() {
+  static const bool v = __builtin_cpu_supports("bmi2") != 0 && __builtin_cpu_supports("adx") != 0;
   return v;
 }
 #endif
@@ -369,7 +415,94 @@ class PoseidonSponge {
       start = 0;
     }
   }
+#ifdef LGH_HAVE_ADX
+  // Width 3, alpha = 17, MDS entries all 0 or 1 (the reference's test sponge): the whole permutation on lazily reduced
+  // values (< 2p) with the ADX product; the three S-boxes of a full round advance level by level, so three independent
+  // products are always in flight (a partial round is one dependent chain of five and stays at the product's latency).
+  // 20.5 k sequential permutations per 2^24-gate proof run here; the state is canonical again on exit.
+  static inline void csub2p_(uint64_t x[4]) {  // x < 4p -> x < 2p
+    static const uint64_t k2P[4] = {0x87c3eb27e0000002ULL, 0x5067d090f372e122ULL, 0x70a08b6d0302b0baULL, 0x60c89ce5c2634053ULL};
+    uint64_t t[4];
+    u128 b = 0;
+    for (int i = 0; i < 4; i++) {
+      const u128 d = (u128)x[i] - k2P[i] - (uint64_t)b;
+      t[i] = (uint64_t)d;
+      b = (d >> 64) & 1;
+    }
+    const uint64_t keep = (uint64_t)0 - (uint64_t)b;  // all ones when x < 2p
+    for (int i = 0; i < 4; i++) x[i] = (x[i] & keep) | (t[i] & ~keep);
+  }
+  static inline void addl_(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {  // a, b < 2p: no overflow, r < 4p
+    u128 c = 0;
+    for (int i = 0; i < 4; i++) {
+      c += (u128)a[i] + b[i];
+      r[i] = (uint64_t)c;
+      c >>= 64;
+    }
+  }
+  bool fast3_ok() const {
+    if (cfg_.rate + cfg_.capacity != 3 || cfg_.alpha != 17 || !cpu_has_adx()) return false;
+    for (uint8_t k : mds_kind_)
+      if (k > 1) return false;
+    static const bool off = getenv("LG_SPONGE_GENERIC") != nullptr;  // tests: force the generic path
+    return !off;
+  }
+  __attribute__((target("bmi2,adx"))) void permute3_adx() {
+    uint64_t st[3][4];
+    for (int i = 0; i < 3; i++) memcpy(st[i], state_[i].l, 32);
+    const int half = cfg_.full_rounds / 2, rounds = cfg_.full_rounds + cfg_.partial_rounds;
+    const Fq* ark = cfg_.ark.data();
+    for (int rnd = 0; rnd < rounds; rnd++, ark += 3) {
+      for (int i = 0; i < 3; i++) {
+        addl_(st[i], st[i], ark[i].l);  // < 2p + p
+        csub2p_(st[i]);
+      }
+      if (rnd < half || rnd >= half + cfg_.partial_rounds) {
+        uint64_t a2[3][4], a4[3][4], a8[3][4], a16[3][4];
+        for (int i = 0; i < 3; i++) mul_adx_lazy(a2[i], st[i], st[i]);
+        for (int i = 0; i < 3; i++) mul_adx_lazy(a4[i], a2[i], a2[i]);
+        for (int i = 0; i < 3; i++) mul_adx_lazy(a8[i], a4[i], a4[i]);
+        for (int i = 0; i < 3; i++) mul_adx_lazy(a16[i], a8[i], a8[i]);
+        for (int i = 0; i < 3; i++) mul_adx_lazy(st[i], a16[i], st[i]);
+      } else {
+        uint64_t a2[4], a4[4], a8[4], a16[4];
+        mul_adx_lazy(a2, st[0], st[0]);
+        mul_adx_lazy(a4, a2, a2);
+        mul_adx_lazy(a8, a4, a4);
+        mul_adx_lazy(a16, a8, a8);
+        mul_adx_lazy(st[0], a16, st[0]);
+      }
+      uint64_t nxt[3][4];
+      for (int i = 0; i < 3; i++) {  // 0/1 matrix: sums of the selected state words, reduced below 2p after every addition
+        bool first = true;
+        const uint8_t* kind = mds_kind_.data() + (size_t)i * 3;
+        for (int j = 0; j < 3; j++) {
+          if (!kind[j]) continue;
+          if (first) {
+            memcpy(nxt[i], st[j], 32);
+            first = false;
+          } else {
+            addl_(nxt[i], nxt[i], st[j]);
+            csub2p_(nxt[i]);
+          }
+        }
+        if (first) memset(nxt[i], 0, 32);
+      }
+      memcpy(st, nxt, sizeof(st));
+    }
+    for (int i = 0; i < 3; i++) {
+      if (geq_p(st[i])) sub_p(st[i]);  // < 2p -> canonical
+      memcpy(state_[i].l, st[i], 32);
+    }
+  }
+#endif
   void permute() {
+#ifdef LGH_HAVE_ADX
+    if (fast3_ok()) {
+      permute3_adx();
+      return;
+    }
+#endif
     const int t = cfg_.rate + cfg_.capacity;
     const int half = cfg_.full_rounds / 2;
     Fq* st = state_.data();

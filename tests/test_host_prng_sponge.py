@@ -57,3 +57,27 @@ def test_sponge_transcripts_match_the_oracle():
                 assert a.squeeze_bytes(n) == b.squeeze_bytes(n), (trial, step, n)
         c = a.clone()
         assert a.squeeze_bytes(32) == b.squeeze_bytes(32) == c.squeeze_bytes(32)
+
+
+def test_sponge_fast_path_equals_generic_path():
+    """The host sponge has a width-3 / alpha-17 fast path (lazy ADX products, host_field.h) next to the generic permutation;
+    LG_SPONGE_GENERIC=1 forces the latter.  Same transcript on a long absorb (an odd count, so the duplex ends mid-rate) and
+    interleaved squeezes; the default path is compared with the oracle above."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import ligero_b200 as lb\n"
+        "s = lb.PoseidonSponge.test_sponge()\n"
+        "s.absorb_bytes(bytes(range(32)))\n"
+        "out = s.squeeze_bytes(32)\n"
+        "s.absorb_field_elements([(i * i * 7919 + 3) %% lb.BN254_R for i in range(1001)])\n"
+        "out += s.squeeze_bytes(64)\n"
+        "s.absorb_field_elements([lb.BN254_R - 1, 0, 1])\n"
+        "print((out + s.squeeze_bytes(32)).hex())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for env in ({}, {"LG_SPONGE_GENERIC": "1"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), check=True)
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] and len(outs[0]) == 256
