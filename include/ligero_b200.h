@@ -267,7 +267,9 @@ typedef struct lg_proof lg_proof;
 int lg_ligero_new(lg_ctx* ctx, const lg_circuit* circuit, const size_t* outputs, size_t n_outputs, size_t lambda, lg_ligero** out);
 int lg_ligero_free(lg_ligero* l);
 /* A LigeroCircuit keeps the device buffers of its last proof (codeword matrix, leaves, tree, [X;Y;Z;W]) so that the next
- * proof of the same circuit re-encodes into them; this returns them to the driver (lg_ligero_free does so too). */
+ * proof of the same circuit re-encodes into them, and the verifier's scratch (r_a in the [X;Y;Z;W] block, one tile of
+ * 1024 encoded rows, the opened columns: 6.3 GiB at 2^24 gates) so that lg_verify allocates nothing after its first call;
+ * this returns all of them to the driver (lg_ligero_free does so too). */
 int lg_ligero_release_buffers(lg_ligero* l);
 int lg_ligero_params(const lg_ligero* l, size_t* m, size_t* k, size_t* n, size_t* t, size_t* sol_len);
 /* witness layout of prove_inner, 476-516: out = Fr[4*m*k] (host) = [X;Y;Z;W].  bump != 0: indices refer to

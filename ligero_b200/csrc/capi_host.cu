@@ -179,7 +179,12 @@ struct lg_ligero {
   // the device trace.  lg_ligero_release_buffers / lg_ligero_free return them.
   lg_matrix* u_cache = nullptr;
   uint64_t* pre_cache = nullptr;
+  // the verifier's device scratch, kept the same way (cudaMalloc / cudaFree of the 4 GiB and 2 GiB blocks per call made
+  // lg_verify at 2^24 gates jitter between 0.33 s and 2 s): see VSlot.  r_a shares pre_cache (same size, never live
+  // at the same time as the prover's matrix).
+  void* vbuf[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+enum VSlot { V_R = 0, V_CHK, V_PLANES, V_COLS, V_RCOLS, V_IDX, V_RQ, V_DIG };
 
 struct lg_proof {
   Digest root;
@@ -673,11 +678,19 @@ bool verify_path(const lg_ctx* ctx, const Digest& root, const Digest& leaf, cons
 // plain cudaMalloc'ed buffer released at scope exit (the verifier returns early on every failed check)
 struct DevMem {
   void* p = nullptr;
+  bool owned = true;
   ~DevMem() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
   }
   int alloc(Ctx* c, size_t bytes) {
     LG_CUDA(c, cudaMalloc(&p, bytes ? bytes : 1));
+    return OK;
+  }
+  // a buffer that lives in *slot (owned by the lg_ligero object) across calls; every slot has one size per circuit
+  int cached(Ctx* c, void** slot, size_t bytes) {
+    if (!*slot) LG_CUDA(c, cudaMalloc(slot, bytes ? bytes : 1));
+    p = *slot;
+    owned = false;
     return OK;
   }
 };
@@ -712,24 +725,20 @@ int verify_openings(lg_ligero* L, const Opened& o, const Digest& root, lgh::Pose
     if (o.auth[q].size() != (size_t)(log_n - 1)) return OK;
   const size_t flat_elems = L->t * rows;
   Ctx* c = &L->ctx->c;
-  Fr* dcols = nullptr;
-  uint8_t* ddig = nullptr;
-  LG_CUDA(c, cudaMalloc(&dcols, flat_elems * sizeof(Fr)));
-  {
-    cudaError_t ea = cudaMalloc(&ddig, L->t * 32);
-    if (ea != cudaSuccess) {  // (do not leak the column buffer when the second allocation fails)
-      cudaFree(dcols);
-      return set_error(c, ERR_NOMEM, std::string("verify_openings cudaMalloc: ") + cudaGetErrorString(ea));
-    }
-  }
+  DevMem mcols, mdig;  // per-circuit scratch of the lg_ligero object: nothing to release on the early returns below
+  LG_TRY(mcols.cached(c, &L->vbuf[V_COLS], flat_elems * sizeof(Fr)));
+  LG_TRY(mdig.cached(c, &L->vbuf[V_DIG], L->t * 32));
+  Fr* dcols = (Fr*)mcols.p;
+  uint8_t* ddig = (uint8_t*)mdig.p;
   std::vector<uint8_t> dig(L->t * 32);
   cudaMemcpyAsync(dcols, o.cols, flat_elems * sizeof(Fr), cudaMemcpyHostToDevice, c->stream);
   int s = hash_column_list(c, dcols, rows, L->t, ddig, L->ctx->col_len_prefix);
   cudaMemcpyAsync(dig.data(), ddig, dig.size(), cudaMemcpyDeviceToHost, c->stream);
   cudaError_t e = cudaStreamSynchronize(c->stream);
-  if (cols_keep) cols_keep->p = dcols;
-  else cudaFree(dcols);
-  cudaFree(ddig);
+  if (cols_keep) {
+    cols_keep->p = dcols;
+    cols_keep->owned = false;
+  }
   if (s != OK) return s;
   if (e != cudaSuccess) return set_error(c, ERR_CUDA, cudaGetErrorString(e));
   for (size_t q = 0; q < L->t; q++) {
@@ -1450,6 +1459,10 @@ int lg_ligero_release_buffers(lg_ligero* L) {
     cudaFree(L->pre_cache);
   }
   L->pre_cache = nullptr;
+  for (void*& b : L->vbuf) {
+    if (b) cudaFree(b);
+    b = nullptr;
+  }
   return OK;
 }
 
@@ -1748,8 +1761,8 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
   std::vector<uint8_t> seed = sp.squeeze_bytes(32);
   cudaSetDevice(c->device);
   DevMem r_dev, chk;
-  LG_TRY(r_dev.alloc(c, rows * sizeof(Fr)));
-  LG_TRY(chk.alloc(c, L->t * sizeof(Fr)));
+  LG_TRY(r_dev.cached(c, &L->vbuf[V_R], rows * sizeof(Fr)));
+  LG_TRY(chk.cached(c, &L->vbuf[V_CHK], 2 * L->t * sizeof(Fr)));  // [0, t): column checks, [t, 2t): polynomial values
   std::vector<Fq> got(L->t);
   // every per-column check below is a dot product over an opened column: one CTA per column on the device
   auto run_checks = [&](int mode, const DevMem& cols, const void* w) -> int {
@@ -1758,15 +1771,31 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
     LG_CUDA(c, cudaStreamSynchronize(c->stream));
     return OK;
   };
-  // a test polynomial (degree < 2k - 1) on the whole n-point domain from its values on the 2k-point domain: one
-  // device encode of a single row of length 2k at rate 2k/n (the opened indices are spread over all cosets)
-  auto on_large_domain = [&](const std::vector<Fq>& evals_2k, std::vector<Fq>& out_n) -> int {
-    lg_matrix* Q = nullptr;
-    LG_TRY(lg_encode(ctx, (const uint64_t*)evals_2k.data(), 1, 2 * k, (uint32_t)(n / (2 * k)), &Q));
-    out_n.resize(n);
-    const int s = lg_matrix_read_rows(Q, 0, 1, (uint64_t*)out_n.data());
-    lg_matrix_free(Q);
-    return s;
+  // a test polynomial (degree < kk) at the t opened indices of the n-point domain, from its values on a kk-point domain
+  // (kk = k or 2k): one device encode of a single row of length kk at rate kk/n into the cached tile buffer, then a gather
+  // of the t entries.  Same values as the reference's full-domain evaluation read at those indices (703-707, 826-829,
+  // 928-932); no allocation, only the t results cross to the host.
+  std::vector<Fq> poly_at(L->t);
+  auto on_large_domain = [&](const std::vector<Fq>& evals, size_t kk, const std::vector<uint64_t>& at) -> int {
+    const size_t tile = rows < 1024 ? rows : 1024;  // 8 * tile * k >= 32k elements: room for the kk inputs and the n outputs
+    DevMem planes, at_dev;
+    LG_TRY(planes.cached(c, &L->vbuf[V_PLANES], 8 * tile * k * sizeof(Fr)));
+    LG_TRY(at_dev.cached(c, &L->vbuf[V_IDX], L->t * sizeof(uint64_t)));
+    int log_kk = 0;
+    while (((size_t)1 << log_kk) < kk) log_kk++;
+    const int rho = (int)(n / kk);
+    Fr* in = (Fr*)planes.p;
+    Fr* p0 = in + kk;
+    LG_CUDA(c, cudaMemcpyAsync(in, evals.data(), kk * sizeof(Fr), cudaMemcpyHostToDevice, c->stream));
+    LG_CUDA(c, cudaMemcpyAsync(at_dev.p, at.data(), L->t * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    LG_TRY(lg::encode_rows(c, in, 1, log_kk, rho, p0, p0 + kk, nullptr, false));
+    Fr* res = (Fr*)chk.p + L->t;
+    gather_tile_columns_kernel<<<64, 256, 0, c->stream>>>(p0, 1, log_kk, rho, (const uint64_t*)at_dev.p, L->t, 0, 1, res);
+    c->launches++;
+    LG_CUDA(c, cudaGetLastError());
+    LG_CUDA(c, cudaMemcpyAsync(poly_at.data(), res, L->t * sizeof(Fr), cudaMemcpyDeviceToHost, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return OK;
   };
   LG_TRY(expand_fr(c, seed.data(), rows, (Fr*)r_dev.p));
   sp.absorb_field(P->preenc_u_lc);
@@ -1779,15 +1808,10 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
     vlap("openings (interleaved)");
     std::vector<Fq> msg(P->preenc_u_lc);  // reed_solomon_interpolate: msg.resize(k) pads or truncates (998-1002)
     msg.resize(k, lgh::kZero);
-    lg_matrix* W = nullptr;
-    LG_TRY(lg_encode(ctx, (const uint64_t*)msg.data(), 1, k, 8, &W));  // reed_solomon(preenc_u_lc)
-    std::vector<Fq> w(n);
-    int s = lg_matrix_read_rows(W, 0, 1, (uint64_t*)w.data());
-    lg_matrix_free(W);
-    if (s != OK) return s;
-    LG_TRY(run_checks(0, cols, r_dev.p));  // <r, column> (705-707)
+    LG_TRY(on_large_domain(msg, k, P->interleaved.leaf_index));  // reed_solomon(preenc_u_lc) at the opened indices
+    LG_TRY(run_checks(0, cols, r_dev.p));                        // <r, column> (705-707)
     for (size_t q = 0; q < L->t; q++)
-      if (w[P->interleaved.leaf_index[q]] != got[q]) return OK;
+      if (poly_at[q] != got[q]) return OK;
     vlap("encode lc + checks");
   }
   // ---- verify_linear (749-830)
@@ -1797,25 +1821,18 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
   // the t columns of each tile are gathered right away: a 2 GiB tile at 2^24 gates instead of a 32 GiB matrix allocated
   // next to the prover's resident one.  Only r_a itself (4mk elements) stays resident in between.
   DevMem ra_dev;
-  LG_TRY(ra_dev.alloc(c, 4 * m * k * sizeof(Fr)));
+  LG_TRY(ra_dev.cached(c, (void**)&L->pre_cache, 4 * m * k * sizeof(Fr)));
   {
     int s = expand_fr(c, seed.data(), 4 * m * k, (Fr*)ra_dev.p);
     if (s == OK) s = lg_sparse_row_mul(ctx, L->a, (const uint64_t*)ra_dev.p, (uint64_t*)ra_dev.p);
     if (s != OK) return s;
     vlap("r_a");
   }
-  auto free_ra = [&]() {
-    if (ra_dev.p) {
-      cudaStreamSynchronize(c->stream);
-      cudaFree(ra_dev.p);
-      ra_dev.p = nullptr;
-    }
-  };
   // columns idx of R_A (t x rows, Montgomery) from row tiles of r_a
   auto gather_ra_columns = [&](const uint64_t* idx_dev, Fr* out) -> int {
     const size_t tile = rows < 1024 ? rows : 1024;
     DevMem planes;
-    LG_TRY(planes.alloc(c, 8 * tile * k * sizeof(Fr)));
+    LG_TRY(planes.cached(c, &L->vbuf[V_PLANES], 8 * tile * k * sizeof(Fr)));
     int log_k = 0;
     while (((size_t)1 << log_k) < k) log_k++;
     for (size_t row0 = 0; row0 < rows; row0 += tile) {
@@ -1831,33 +1848,24 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
   };
   const std::vector<Fq>& ql = P->linear_poly;
   const size_t deg_l = ql.empty() ? 0 : ql.size() - 1;
-  if (deg_l >= 2 * k - 1) {
-    free_ra();
-    return OK;
-  }
+  if (deg_l >= 2 * k - 1) return OK;
   std::vector<Fq> ie(ql);
   ie.resize(2 * k, lgh::kZero);
   host_fft(ie, false);
   {
     Fq sum = lgh::kZero;
     for (size_t i = 0; i < 2 * k; i += 2) sum = lgh::add(sum, ie[i]);
-    if (!sum.is_zero()) {
-      free_ra();
-      return OK;
-    }
+    if (!sum.is_zero()) return OK;
   }
   sp.absorb_field(ql);
   vlap("host fft + absorb linear");
   {
     DevMem cols, rcols, idx_dev;
     int s = verify_openings(L, P->linear, P->root, sp, &ok, &cols);
-    if (s != OK || !ok) {
-      free_ra();
-      return s;
-    }
+    if (s != OK || !ok) return s;
     // the same columns of R_A, gathered on the device, then <R_A column, U column> per opened column (822-829)
-    s = rcols.alloc(c, L->t * rows * sizeof(Fr));
-    if (s == OK) s = idx_dev.alloc(c, L->t * sizeof(uint64_t));
+    s = rcols.cached(c, &L->vbuf[V_RCOLS], L->t * rows * sizeof(Fr));
+    if (s == OK) s = idx_dev.cached(c, &L->vbuf[V_IDX], L->t * sizeof(uint64_t));
     if (s == OK && cudaMemcpyAsync(idx_dev.p, P->linear.leaf_index.data(), L->t * sizeof(uint64_t), cudaMemcpyHostToDevice,
                                    c->stream) != cudaSuccess)
       s = fail(ctx, ERR_CUDA, "index upload failed");
@@ -1865,17 +1873,15 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
     vlap("R_A row tiles: encode + gather");
     if (s == OK) s = run_checks(1, cols, rcols.p);
     vlap("checks (linear)");
-    free_ra();
     if (s != OK) return s;
-    std::vector<Fq> q_n;
-    LG_TRY(on_large_domain(ie, q_n));
+    LG_TRY(on_large_domain(ie, 2 * k, P->linear.leaf_index));
     for (size_t q = 0; q < L->t; q++)
-      if (got[q] != q_n[P->linear.leaf_index[q]]) return OK;
+      if (got[q] != poly_at[q]) return OK;
   }
   // ---- verify_quadratic_constraints (861-933)
   seed = sp.squeeze_bytes(32);
   DevMem rq_dev;
-  LG_TRY(rq_dev.alloc(c, m * sizeof(Fr)));
+  LG_TRY(rq_dev.cached(c, &L->vbuf[V_RQ], m * sizeof(Fr)));
   LG_TRY(expand_fr(c, seed.data(), m, (Fr*)rq_dev.p));
   const std::vector<Fq>& qq = P->quadratic_poly;
   const size_t deg_q = qq.empty() ? 0 : qq.size() - 1;
@@ -1892,10 +1898,10 @@ static int lg_verify_impl(lg_ligero* L, const lg_proof* P, lg_sponge* sponge, in
     if (!ok) return OK;
     LG_TRY(run_checks(2, cols, rq_dev.p));  // sum_i r_i (x_i y_i - z_i) per opened column (909-932)
     vlap("quadratic: fft, absorb, openings, checks");
-    std::vector<Fq> q_n;
-    LG_TRY(on_large_domain(iq, q_n));
+    LG_TRY(on_large_domain(iq, 2 * k, P->quadratic.leaf_index));
     for (size_t q = 0; q < L->t; q++)
-      if (q_n[P->quadratic.leaf_index[q]] != got[q]) return OK;
+      if (poly_at[q] != got[q]) return OK;
+    vlap("quadratic polynomial on the large domain");
   }
   *accepted = 1;
   return OK;
