@@ -18,19 +18,19 @@
 #include <vector>
 
 #include "capi_types.h"
+#include "circuit_host.h"
 #include "host_field.h"
 #include "host_prng.h"
 
 using namespace lg;
 using lgh::Fq;
+using lgh::N_ADD;
+using lgh::N_CONST;
+using lgh::N_MUL;
+using lgh::N_VAR;
+using lgh::Node;  // circuit_host.h
 
 namespace {
-
-enum NodeType : uint8_t { N_VAR = 0, N_CONST = 1, N_ADD = 2, N_MUL = 3 };
-struct Node {
-  uint8_t type;
-  uint64_t l, r;  // operands; for N_CONST l = index into const_values; for N_VAR l = index into labels
-};
 
 typedef std::array<uint8_t, 32> Digest;
 
@@ -139,7 +139,7 @@ struct Opened {
 }  // namespace
 
 struct lg_circuit {
-  std::vector<Node> nodes;
+  lgh::RawVec<Node> nodes;  // (a vector whose resize() does not zero: LigeroCircuit::new fills its copy on all host threads)
   std::vector<Fq> const_values;
   std::vector<std::string> labels;
   std::map<Fq, size_t> constants;            // value -> node index
@@ -166,9 +166,9 @@ struct lg_ligero {
   lg_constraints* a = nullptr;
   // evaluation trace on the device (trace.cu): level schedule, reachability from the outputs, witness slots
   lg::TraceSchedule trace;
-  std::vector<uint32_t> index_map;  // node -> slot in the X/Y/Z/W blocks (0xffffffff for dropped constants)
-  std::vector<uint8_t> reach;       // node feeds an output
-  std::vector<uint32_t> var_nodes;  // every Variable node
+  lgh::RawVec<uint32_t> index_map;  // node -> slot in the X/Y/Z/W blocks (0xffffffff for dropped constants)
+  lgh::RawVec<uint8_t> reach;       // node feeds an output
+  lgh::RawVec<uint32_t> var_nodes;  // every Variable node
   bool all_gates_reach = true;
   int trace_mode = -1;              // -1: by circuit shape, 0: host evaluator, 1: device
   // host wall clock of the last prove, ms: trace+layout, commit, interleaved test, linear test, quadratic test,
@@ -200,14 +200,7 @@ namespace {
 
 int fail(lg_ctx* ctx, int code, const std::string& msg) { return set_error(ctx ? &ctx->c : nullptr, code, msg); }
 
-size_t bump_index(size_t one_index, bool one_found, size_t index) {  // src/ligero/mod.rs:230-242
-  if (one_found) {
-    if (index < one_index) return index + 1;
-    if (index == one_index) return 0;
-    return index;
-  }
-  return index + 1;
-}
+using lgh::bump_index;  // src/ligero/mod.rs:230-242 (circuit_host.h)
 
 size_t calculate_t(size_t sec_param, size_t d_num, size_t d_den, size_t codeword_len) {
   const double residual = (double)codeword_len / std::pow(2.0, 254);
@@ -342,7 +335,7 @@ bool debug_timing() {
   return e && atoi(e) != 0;
 }
 
-int build_constraints(lg_ligero* L, std::string& err) {
+int build_constraints(lg_ligero* L, const lgh::NodeArrays& arr, std::string& err) {
   const lg_circuit& c = L->circuit;
   const auto& nodes = c.nodes;
   const size_t mk = L->m * L->k;
@@ -350,11 +343,11 @@ int build_constraints(lg_ligero* L, std::string& err) {
   std::vector<Fq> table;
   constant_value_ids(c, vidp, vidn, table);
   // the reference panics on these (mod.rs:325, 345, 369-414): refuse them before building anything
-  for (size_t i = 0; i < nodes.size(); i++) {
-    const Node& nd = nodes[i];
-    if ((nd.type == N_ADD || nd.type == N_MUL) && nodes[nd.l].type == N_CONST && nodes[nd.r].type == N_CONST) {
-      err = nd.type == N_ADD ? "Add(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:325)"
-                             : "Mul(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:345)";
+  {
+    const size_t i = lgh::first_gate_of_two_constants(arr, lgh::host_threads());
+    if (i != SIZE_MAX) {
+      err = nodes[i].type == N_ADD ? "Add(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:325)"
+                                   : "Mul(constant, constant) is not supported (the reference panics at src/ligero/mod.rs:345)";
       return ERR_UNSUPPORTED;
     }
   }
@@ -369,19 +362,12 @@ int build_constraints(lg_ligero* L, std::string& err) {
   bool on_device = nodes.size() >= ((size_t)1 << 16);
   if (const char* e = getenv("LG_CSC_DEVICE")) on_device = atoi(e) != 0;
   if (on_device) {
-    const double t0 = now_ms();
-    std::vector<uint8_t> type(nodes.size());
-    std::vector<uint32_t> l(nodes.size()), r(nodes.size()), outs(L->outputs.begin(), L->outputs.end());
-    for (size_t i = 0; i < nodes.size(); i++) {
-      type[i] = nodes[i].type;
-      l[i] = (uint32_t)nodes[i].l;
-      r[i] = (uint32_t)nodes[i].r;
-    }
     const double t1 = now_ms();
-    const int s = lg::build_constraints_device(L->ctx, type.data(), l.data(), r.data(), nodes.size(), vidp.data(), vidn.data(), vidp.size(),
+    std::vector<uint32_t> outs(L->outputs.begin(), L->outputs.end());
+    const int s = lg::build_constraints_device(L->ctx, arr.type.get(), arr.l.get(), arr.r.get(), arr.n, vidp.data(), vidn.data(), vidp.size(),
                                                outs.data(), outs.size(), mk, table.empty() ? nullptr : (const uint64_t*)table.data(),
                                                table.size(), &L->a);
-    if (debug_timing()) fprintf(stderr, "[lg] constraint matrix on the device: node arrays %.1f ms, build %.1f ms\n", t1 - t0, now_ms() - t1);
+    if (debug_timing()) fprintf(stderr, "[lg] constraint matrix on the device: build %.1f ms\n", now_ms() - t1);
     if (s != OK) err = lg_last_error(L->ctx);
     return s;
   }
@@ -468,8 +454,8 @@ int build_constraints(lg_ligero* L, std::string& err) {
 // ---- level schedule of the circuit for the device evaluator (trace.cu) ----------------------------------
 constexpr size_t kNarrowLevel = 2048;  // levels of at most this many gates are walked by a single CTA
 
-template <class T>
-int upload(lg_ctx* ctx, const std::vector<T>& v, T** out) {
+template <class V, class T = typename V::value_type>
+int upload(lg_ctx* ctx, const V& v, T** out) {
   *out = nullptr;
   if (v.empty()) return OK;
   if (cudaMalloc((void**)out, v.size() * sizeof(T)) != cudaSuccess) {
@@ -481,77 +467,32 @@ int upload(lg_ctx* ctx, const std::vector<T>& v, T** out) {
   return OK;
 }
 
-int build_trace(lg_ligero* L) {
+int build_trace(lg_ligero* L, const lgh::NodeArrays& arr) {
   const lg_circuit& c = L->circuit;
   const auto& nodes = c.nodes;
   const size_t N = nodes.size();
-  if (N >= 0x7fffffffu) return fail(L->ctx, ERR_UNSUPPORTED, "circuits of 2^31 nodes or more are not supported");
   cudaSetDevice(L->ctx->c.device);
-  // node -> witness slot (mod.rs:483-504: constants other than node 0 own no slot)
-  L->index_map.assign(N, 0xffffffffu);
-  L->index_map[0] = 0;
-  size_t seen = 0;
-  for (size_t i = 1; i < N; i++) {
-    if (nodes[i].type == N_CONST) seen++;
-    else L->index_map[i] = (uint32_t)(i - seen);
-  }
-  // which nodes feed an output (the reference panics at prove time on any that does not, mod.rs:476-478)
-  L->reach.assign(N, 0);
-  for (size_t o : L->outputs) L->reach[o] = 1;
-  L->all_gates_reach = true;
-  for (size_t i = N; i-- > 0;) {
-    const Node& nd = nodes[i];
-    if (nd.type != N_ADD && nd.type != N_MUL) continue;
-    if (L->reach[i]) L->reach[nd.l] = L->reach[nd.r] = 1;
-    else L->all_gates_reach = false;
-  }
-  // levels: operands always precede a gate (ArithmeticCircuit only appends), so one forward sweep
-  std::vector<uint32_t> level(N, 0);
-  uint32_t depth = 0;
-  size_t n_gates = 0;
-  for (size_t i = 0; i < N; i++) {
-    const Node& nd = nodes[i];
-    if (nd.type != N_ADD && nd.type != N_MUL) continue;
-    level[i] = 1 + std::max(level[nd.l], level[nd.r]);
-    depth = std::max(depth, level[i]);
-    n_gates++;
-  }
+  // slot map, reachability from the outputs, levels and the gates sorted by (level, Add before Mul): circuit_host.h
+  lgh::Schedule sch;
+  lgh::build_schedule(arr, L->outputs.data(), L->outputs.size(), sch, lgh::host_threads());
+  L->index_map = std::move(sch.index_map);
+  L->reach = std::move(sch.reach);
+  L->all_gates_reach = sch.all_gates_reach;
+  L->var_nodes = std::move(sch.var_nodes);
+  const size_t depth = sch.depth;
+  const std::vector<uint32_t>& level_start = sch.level_start;
   lg::TraceSchedule& t = L->trace;
   t.n_nodes = N;
-  t.n_gates = n_gates;
-  t.n_levels = depth;
+  t.n_gates = sch.n_gates;
+  t.n_levels = sch.depth;
   t.mk = L->m * L->k;
-  // counting sort by (level, Add before Mul)
-  std::vector<uint32_t> start(2 * (size_t)depth + 1, 0);
-  for (size_t i = 0; i < N; i++)
-    if (nodes[i].type == N_ADD || nodes[i].type == N_MUL) start[2 * (level[i] - 1) + (nodes[i].type == N_MUL) + 1]++;
-  for (size_t b = 0; b < 2 * (size_t)depth; b++) start[b + 1] += start[b];
-  std::vector<uint32_t> level_start(depth + 1);
-  for (size_t l = 0; l <= depth; l++) level_start[l] = start[2 * l];
-  std::vector<uint32_t> gnode(n_gates), gl(n_gates), gr(n_gates), gpos(n_gates);
-  {
-    std::vector<uint32_t> cursor(start.begin(), start.end() - 1);
-    for (size_t i = 0; i < N; i++) {
-      const Node& nd = nodes[i];
-      if (nd.type != N_ADD && nd.type != N_MUL) continue;
-      const uint32_t g = cursor[2 * (level[i] - 1) + (nd.type == N_MUL)]++;
-      gnode[g] = (uint32_t)i | (nd.type == N_MUL ? 0x80000000u : 0u);
-      gl[g] = (uint32_t)nd.l;
-      gr[g] = (uint32_t)nd.r;
-      gpos[g] = L->index_map[i];
-    }
+  const lgh::RawVec<uint32_t>&gnode = sch.gate_node, &gl = sch.gate_l, &gr = sch.gate_r, &gpos = sch.gate_pos, &cnode = sch.const_nodes;
+  std::vector<uint32_t> cpos(cnode.size());
+  std::vector<Fq> cval(cnode.size());
+  for (size_t j = 0; j < cnode.size(); j++) {
+    cpos[j] = L->index_map[cnode[j]];
+    cval[j] = c.const_values[nodes[cnode[j]].l];
   }
-  std::vector<uint32_t> cnode, cpos;
-  std::vector<Fq> cval;
-  L->var_nodes.clear();
-  for (size_t i = 0; i < N; i++)
-    if (nodes[i].type == N_VAR) L->var_nodes.push_back((uint32_t)i);
-  for (size_t i = 0; i < N; i++)
-    if (nodes[i].type == N_CONST) {
-      cnode.push_back((uint32_t)i);
-      cpos.push_back(L->index_map[i]);
-      cval.push_back(c.const_values[nodes[i].l]);
-    }
   t.n_consts = cnode.size();
   // segments: wide levels get a launch each, runs of narrow levels share a single-CTA launch
   t.segments.clear();
@@ -1370,8 +1311,12 @@ static int lg_ligero_new_impl(lg_ctx* ctx, const lg_circuit* circuit, const size
   lg_ligero* L = new (std::nothrow) lg_ligero();
   if (!L) return ERR_NOMEM;
   L->ctx = ctx;
-  L->circuit = *circuit;
-  lg_circuit& c = L->circuit;
+  lg_circuit& c = L->circuit;  // the formatted copy; its nodes are written below, already in their final places
+  c.const_values = circuit->const_values;
+  c.labels = circuit->labels;
+  c.constants = circuit->constants;
+  c.variables = circuit->variables;
+  c.error = circuit->error;
   auto it = c.constants.find(lgh::kOne);
   if (it != c.constants.end()) {
     L->one_index = it->second;
@@ -1382,26 +1327,20 @@ static int lg_ligero_new_impl(lg_ctx* ctx, const lg_circuit* circuit, const size
   }
   const size_t oi = L->one_index;
   const bool of = L->one_found;
+  Node one_node{N_CONST, 0, 0};
   if (oi != 0) {  // insert_one (mod.rs:244-271)
-    if (of) {
-      c.nodes.erase(c.nodes.begin() + oi);
-    } else {
-      c.const_values.push_back(lgh::kOne);
-    }
-    Node one_node{N_CONST, 0, 0};
     if (of) {
       // keep the existing const_values slot of the constant 1
       for (size_t j = 0; j < c.const_values.size(); j++)
         if (c.const_values[j] == lgh::kOne) one_node.l = j;
     } else {
+      c.const_values.push_back(lgh::kOne);
       one_node.l = c.const_values.size() - 1;
     }
-    c.nodes.insert(c.nodes.begin(), one_node);
-    for (auto& nd : c.nodes)
-      if (nd.type == N_ADD || nd.type == N_MUL) {
-        nd.l = bump_index(oi, of, nd.l);
-        nd.r = bump_index(oi, of, nd.r);
-      }
+  }
+  // the caller's constant 1 (if any) removed, the constant 1 in front, the operands of every gate bumped: one pass
+  lgh::format_nodes(circuit->nodes.data(), circuit->nodes.size(), oi, of, one_node, c.nodes, lgh::host_threads());
+  if (oi != 0) {
     for (auto& kv : c.constants) kv.second = bump_index(oi, of, kv.second);
     c.constants[lgh::kOne] = 0;
     for (auto& kv : c.variables) kv.second = bump_index(oi, of, kv.second);
@@ -1425,19 +1364,26 @@ static int lg_ligero_new_impl(lg_ctx* ctx, const lg_circuit* circuit, const size
     }
     L->outputs.push_back(o);
   }
+  if (c.nodes.size() >= 0x7fffffffu) {
+    delete L;
+    return fail(ctx, ERR_UNSUPPORTED, "circuits of 2^31 nodes or more are not supported");
+  }
   std::string err;
+  const double t_c00 = now_ms();
+  lgh::NodeArrays arr;  // type / left / right as flat arrays: what every pass below reads instead of the 24-byte nodes
+  lgh::pack_nodes(c.nodes.data(), c.nodes.size(), arr, lgh::host_threads());
   const double t_c0 = now_ms();
-  int s = build_constraints(L, err);
+  int s = build_constraints(L, arr, err);
   const double t_c1 = now_ms();
   if (s != OK) {
     if (!err.empty()) fail(ctx, s, err);
     lg_ligero_free(L);
     return s;
   }
-  s = build_trace(L);
+  s = build_trace(L, arr);
   if (debug_timing())
-    fprintf(stderr, "[lg] LigeroCircuit::new: constraint matrix %.1f ms, trace schedule %.1f ms (%zu nodes)\n", t_c1 - t_c0, now_ms() - t_c1,
-            c.nodes.size());
+    fprintf(stderr, "[lg] LigeroCircuit::new: node arrays %.1f ms, constraint matrix %.1f ms, trace schedule %.1f ms (%zu nodes, %d host threads)\n",
+            t_c0 - t_c00, t_c1 - t_c0, now_ms() - t_c1, c.nodes.size(), lgh::host_threads());
   if (s != OK) {
     lg_ligero_free(L);
     return s;

@@ -32,3 +32,14 @@ def test_host_field_against_python_integers(tmp_path):
             cur = {}
         cur[k] = int(v, 16)
     assert n == 4000
+
+
+def test_circuit_host_passes_against_plain_loops(tmp_path):
+    """ligero_b200/csrc/circuit_host.h (the threaded host passes of LigeroCircuit::new: formatted node copy, compact node arrays,
+    the constant-constant gate check, slot map, reachability, level schedule) against single-threaded statements of the same arrays,
+    on random, deep, chain-shaped and gate-less circuits at 1, 2, 3 and 8 threads (src/ligero/mod.rs:179-194, 230-271, 476-478)."""
+    exe = os.path.join(str(tmp_path), "circuit_host_test")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "host", "circuit_host_test.cpp")], check=True)
+    for seed in ("1", "20240"):
+        out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
+        assert out.startswith("CIRCUIT_HOST_OK 144"), out
