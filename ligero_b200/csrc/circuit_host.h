@@ -183,30 +183,106 @@ struct Schedule {
 
 namespace detail {
 
+// Level of every gate = 1 + the larger level of its operands (operands always precede a gate: ArithmeticCircuit only
+// appends).  One forward sweep settles them, but it is a chain of random reads that one core's miss queue bounds (10 ns
+// per gate), so the sweep goes block by block: inside a block of 2^17 nodes all threads take the gates whose operands both
+// lie before the block (their levels are final), and the few gates with an operand inside the block are finished by
+// one thread in index order afterwards.  `level` must be zero on entry.  false if a level does not fit LT.
+template <class LT>
+bool compute_levels(const NodeArrays& a, LT* level, int threads, uint32_t* depth_out, size_t* gates_out) {
+  const size_t N = a.n;
+  const uint8_t* type = a.type.get();
+  const uint32_t *L = a.l.get(), *R = a.r.get();
+  const uint32_t level_max = (uint32_t)(LT)~(LT)0;
+  const int chunks = chunk_count(N, threads);
+  uint32_t depth = 0;
+  size_t n_gates = 0;
+  if (chunks == 1) {
+    for (size_t i = 0; i < N; i++) {
+      if (type[i] < N_ADD) continue;
+      const uint32_t v = 1u + std::max<uint32_t>(level[L[i]], level[R[i]]);
+      if (v > level_max) return false;
+      level[i] = (LT)v;
+      depth = std::max(depth, v);
+      n_gates++;
+    }
+    *depth_out = depth;
+    *gates_out = n_gates;
+    return true;
+  }
+  constexpr size_t kBlock = (size_t)1 << 17;
+  std::vector<uint32_t> deferred(kBlock);  // gates left to the sequential step; thread t writes from seg_lo[t] on
+  std::vector<size_t> seg_lo((size_t)chunks, 0), n_def((size_t)chunks, 0), gates((size_t)chunks, 0);
+  std::vector<uint32_t> deepest((size_t)chunks, 0);
+  std::vector<uint8_t> over((size_t)chunks, 0);
+  uint32_t* def_all = deferred.data();
+  size_t *p_lo = seg_lo.data(), *p_nd = n_def.data(), *p_g = gates.data();
+  uint32_t* p_deep = deepest.data();
+  uint8_t* p_over = over.data();
+  for (size_t b0 = 0; b0 < N; b0 += kBlock) {
+    const size_t bn = std::min(kBlock, N - b0);
+    parallel_chunks(bn, chunks, [=](int t, size_t lo, size_t hi) {
+      uint32_t* def = def_all + lo;
+      size_t nd = 0, g = 0;
+      uint32_t dp = p_deep[t];
+      for (size_t j = lo; j < hi; j++) {
+        const size_t i = b0 + j;
+        if (type[i] < N_ADD) continue;
+        g++;
+        const uint32_t l = L[i], r = R[i];
+        if (l >= b0 || r >= b0) {
+          def[nd++] = (uint32_t)i;
+          continue;
+        }
+        const uint32_t v = 1u + std::max<uint32_t>(level[l], level[r]);
+        if (v > level_max) {
+          p_over[t] = 1;
+          continue;
+        }
+        level[i] = (LT)v;
+        dp = std::max(dp, v);
+      }
+      p_lo[t] = lo;
+      p_nd[t] = nd;
+      p_g[t] += g;
+      p_deep[t] = dp;
+    });
+    for (int t = 0; t < chunks; t++) {
+      if (over[(size_t)t]) return false;
+      const uint32_t* def = def_all + seg_lo[(size_t)t];
+      for (size_t q = 0; q < n_def[(size_t)t]; q++) {
+        const size_t i = def[q];
+        const uint32_t v = 1u + std::max<uint32_t>(level[L[i]], level[R[i]]);
+        if (v > level_max) return false;
+        level[i] = (LT)v;
+        depth = std::max(depth, v);
+      }
+    }
+  }
+  for (int t = 0; t < chunks; t++) {
+    depth = std::max(depth, deepest[(size_t)t]);
+    n_gates += gates[(size_t)t];
+  }
+  *depth_out = depth;
+  *gates_out = n_gates;
+  return true;
+}
+
 // levels + counting sort, with the level of a node held in LT; false if a level does not fit (nothing is kept then)
 template <class LT>
 bool schedule_gates(const NodeArrays& a, Schedule& s, int threads) {
   const size_t N = a.n;
   const uint8_t* type = a.type.get();
   const uint32_t *L = a.l.get(), *R = a.r.get();
-  const uint32_t level_max = (uint32_t)(LT)~(LT)0;
   RawVec<LT> level(N);
   {
     const int chunks = chunk_count(N, threads);
     LT* lv = level.data();
     parallel_chunks(N, chunks, [=](int, size_t lo, size_t hi) { memset(lv + lo, 0, (hi - lo) * sizeof(LT)); });
   }
-  // operands always precede a gate (ArithmeticCircuit only appends), so one forward sweep settles every level
   uint32_t depth = 0;
   size_t n_gates = 0;
-  for (size_t i = 0; i < N; i++) {
-    if (type[i] < N_ADD) continue;
-    const uint32_t v = 1u + std::max<uint32_t>(level[L[i]], level[R[i]]);
-    if (v > level_max) return false;
-    level[i] = (LT)v;
-    depth = std::max(depth, v);
-    n_gates++;
-  }
+  if (!compute_levels<LT>(a, level.data(), threads, &depth, &n_gates)) return false;
   s.depth = depth;
   s.n_gates = n_gates;
   const size_t B = 2 * (size_t)depth;  // bucket of a gate: 2 * (level - 1) + (Mul ? 1 : 0)

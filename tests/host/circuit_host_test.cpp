@@ -162,7 +162,7 @@ int main(int argc, char** argv) {
   int cases = 0;
   // sizes on both sides of the 65 536-node threshold below which everything runs on one chunk; a 70 000-gate chain has
   // more than 65 535 levels (the 16-bit level table overflows and the 32-bit one takes over)
-  const size_t sizes[] = {2, 3, 7, 100, 5000, 65535, 65536, 70001, 200003};
+  const size_t sizes[] = {2, 3, 7, 100, 5000, 65535, 65536, 70001, 200003, 600011};  // the last two span 2 and 5 level blocks
   for (size_t n : sizes)
     for (int shape = 0; shape < 4; shape++)
       for (int threads : {1, 2, 3, 8}) {

@@ -42,4 +42,4 @@ def test_circuit_host_passes_against_plain_loops(tmp_path):
     subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "host", "circuit_host_test.cpp")], check=True)
     for seed in ("1", "20240"):
         out = subprocess.run([exe, seed], check=True, capture_output=True, text=True).stdout
-        assert out.startswith("CIRCUIT_HOST_OK 144"), out
+        assert out.startswith("CIRCUIT_HOST_OK 160"), out
