@@ -52,6 +52,11 @@ def _ptr(x) -> c_void_p:
         return c_void_p(x.ctypes.data)
     if hasattr(x, "data_ptr"):
         assert x.is_contiguous()
+        if getattr(x, "is_cuda", False):
+            # the library launches on its own non-blocking stream, which does not wait for torch's: whatever torch still
+            # has in flight for this tensor must be finished before the pointer is handed over
+            import torch
+            torch.cuda.current_stream(x.device).synchronize()
         return c_void_p(x.data_ptr())
     return c_void_p(int(x))
 
