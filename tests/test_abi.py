@@ -68,8 +68,8 @@ def test_nothing_at_run_time_reads_the_reference_tree():
 
 
 def test_header_is_valid_c_and_the_c_host_example_links():
-    """include/ligero_b200.h compiled as C11 by gcc, and tests/c/mgpu_prove.c (a C host driving lg_mgpu_prove) linked
-    against the in-tree library; without a GPU the program stops at lg_ctx_create with LG_ERR_CUDA -- no CPU fallback."""
+    """include/ligero_b200.h compiled as C11 by gcc, and tests/c/mgpu_prove.c (a C host driving lg_mgpu_prove) and
+    tests/c/new_prove_check.c (LigeroCircuit::new / prove / verify from C) linked against the in-tree library; without a GPU the program stops at lg_ctx_create with LG_ERR_CUDA -- no CPU fallback."""
     import subprocess
     import tempfile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -80,7 +80,14 @@ def test_header_is_valid_c_and_the_c_host_example_links():
                             os.path.join(root, "tests", "c", "mgpu_prove.c"), "-o", exe, "-L", libdir, "-lligero_b200",
                             f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+        exe2 = os.path.join(tmp, "new_prove_check")
+        r = subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                            os.path.join(root, "tests", "c", "new_prove_check.c"), "-o", exe2, "-L", libdir, "-lligero_b200",
+                            f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
         import torch
         if not torch.cuda.is_available():
             run = subprocess.run([exe, "1", "6"], capture_output=True, text=True)
+            assert run.returncode != 0 and "lg_ctx_create" in run.stderr
+            run = subprocess.run([exe2, "8"], capture_output=True, text=True)
             assert run.returncode != 0 and "lg_ctx_create" in run.stderr

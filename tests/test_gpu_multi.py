@@ -68,3 +68,17 @@ def test_c_host_drives_the_multi_gpu_prover(n, tmp_path):
         pytest.skip(f"needs {n} GPUs")
     r = run([build_c_host(tmp_path), str(n), "14"])
     assert "C_MGPU_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("log_gates", [10, 17])
+def test_c_host_new_prove_verify(log_gates, tmp_path):
+    """tests/c/new_prove_check.c on one GPU: LigeroCircuit::new through the C ABI (2^17 gates: constraint matrix built on the
+    device, level schedule from the threaded host passes of circuit_host.h; 2^10: the host builders), the proof with the trace
+    evaluated on the device equals the proof with the host evaluator byte for byte, and verifies (src/ligero/mod.rs:147-228, 435-455)."""
+    exe = str(tmp_path / "new_prove_check")
+    libdir = os.path.join(ROOT, "ligero_b200")
+    r = run(["gcc", "-std=c11", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "new_prove_check.c"), "-o", exe,
+             "-L", libdir, "-lligero_b200", f"-Wl,-rpath,{libdir}"])
+    assert r.returncode == 0, r.stderr
+    r = run([exe, str(log_gates)])
+    assert "C_NEW_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
