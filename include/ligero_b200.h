@@ -296,7 +296,8 @@ int lg_prove_with_labels(lg_ligero* l, const char* const* labels, const uint64_t
                          lg_proof** out);
 /* the commit-and-test transcript on a ready pre-encoding matrix (Fr[4*m*k], host or device) */
 int lg_prove_matrix(lg_ligero* l, const uint64_t* preenc_u, lg_sponge* sponge, lg_proof** out);
-/* verify, 613-644: *accepted = 1 iff every check passes (0 otherwise; errors only for resource failures) */
+/* verify, 613-644: *accepted = 1 iff every check passes (0 otherwise; errors only for resource failures).  Uses the
+ * scratch of `l` (see lg_ligero_release_buffers): one lg_prove / lg_verify at a time per lg_ligero, like everything on a ctx. */
 int lg_verify(lg_ligero* l, const lg_proof* proof, lg_sponge* sponge, int* accepted);
 int lg_proof_free(lg_proof* p);
 /* borrowed handle of the circuit's constraint matrix A on the device (owned by the lg_ligero) */
